@@ -1,0 +1,210 @@
+/*
+ * cq_b200.h -- C-ABI of libcq_b200.so: runtime-quadrature finite-element assembly
+ * (customquad's assemble_matrix / assemble_vector / assemble_scalar) on one B200.
+ *
+ * Boundary rules:
+ *   - extern "C" only, plain pointers and sizes, no torch / C++ types.
+ *   - every function returns int: 0 = CQ_OK, negative = cq_status; cq_last_error()
+ *     gives a thread-local message.  Nothing throws or exits across the boundary.
+ *   - all array arguments of the cq_assemble_* entry points are caller-owned DEVICE
+ *     pointers on the device the ctx was created for (the *_host entry points take
+ *     HOST pointers and do their own staged copies); the library allocates nothing
+ *     persistent except the opaque cq_ctx (scratch, error flag, copy streams).
+ *   - calls are asynchronous and ordered on the cudaStream_t passed in (as void*).
+ *
+ * What each entry point replaces in the reference (paths into /root/reference):
+ *   cq_assemble_matrix  <- customquad/assemble_matrix.py:50-113 (assemble_cells: gather,
+ *                          generated tabulate_tensor_runtime_float64, MatSetValuesLocal ADD)
+ *                          + customquad/call_basix.h:14-81 (basis tables at runtime points)
+ *                          + customquad/setup_types.py:106-113 (MatSetValuesLocal binding)
+ *   cq_assemble_vector  <- customquad/assemble_vector.py:52-94
+ *   cq_assemble_scalar  <- customquad/assemble_scalar.py:37-82
+ *   cq_tabulate         <- customquad/call_basix.h:14-81 alone (debug / parity hook; the
+ *                          analogue of its debug_output dump, call_basix.h:83-126)
+ *   cq_element_tensors  <- one generated-kernel call per cell, README.md:133-158, without
+ *                          the scatter (the analogue of utils.print_for_header, utils.py:185-225)
+ *   cq_csr_accumulate_rows <- the receive side of PETSc MatAssemblyBegin/End after
+ *                          A.assemble() (README.md:95, demo/poisson.py:194)
+ */
+#ifndef CQ_B200_H
+#define CQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CQ_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------ */
+typedef enum cq_status {
+  CQ_OK = 0,
+  CQ_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported cell/degree/form ...) */
+  CQ_ERR_CUDA = -2,        /* a CUDA runtime call failed; see cq_last_error()               */
+  CQ_ERR_UNSUPPORTED = -3, /* combination not implemented                                   */
+  CQ_ERR_SPARSITY = -4,    /* a (row, col) produced by a cell is absent from the CSR pattern */
+  CQ_ERR_ALIGN = -5        /* pointer alignment requirement violated (8 B for all f64/i64)   */
+} cq_status;
+
+/* ---- what is integrated --------------------------------------------------------------
+ * The reference gets its integrand from UFL through ffcx-custom; there is no UFL here, so
+ * the integrand is one of the forms the reference's demos and tests use. */
+typedef enum cq_form {
+  /* rank 2 -> cq_assemble_matrix */
+  CQ_FORM_MASS = 0,        /* inner(u, v)                         test/common.py:91            */
+  CQ_FORM_STIFFNESS = 1,   /* inner(grad u, grad v)               demo/poisson.py:154          */
+  CQ_FORM_NITSCHE = 2,     /* -(n.grad u) v - u (n.grad v) + betaN/h u v  demo/poisson.py:156-158 */
+  /* rank 1 -> cq_assemble_vector */
+  CQ_FORM_LOAD = 10,       /* inner(f, v)      demo/poisson.py:155, test/common.py:68, test_linear_basis.py:129 */
+  CQ_FORM_NITSCHE_RHS = 11,/* -g (n.grad v) + betaN/h g v         demo/poisson.py:159          */
+  /* rank 0 -> cq_assemble_scalar */
+  CQ_FORM_INTEGRAL = 20,   /* f                test_volume_area.py:58, test_linear_basis.py:84-86 */
+  CQ_FORM_INTEGRAL_SQ = 21,/* inner(f, f)      test/common.py:44                               */
+  CQ_FORM_L2_ERR = 22,     /* (uh - u_ex)**2   demo/poisson.py:275                             */
+  CQ_FORM_H10_ERR = 23     /* (grad uh - grad u_ex)**2   demo/poisson.py:279                   */
+} cq_form;
+
+/* The data function f / g / u_ex of a form.  CQ_FN_COEF is a finite-element function of the
+ * form's own space (packed per cell like dolfinx.cpp.fem.pack_coefficients,
+ * assemble_matrix.py:16,92); the others are closed-form in the physical coordinate x
+ * (ufl.SpatialCoordinate in the reference) with parameters in `consts`. Component a of a
+ * blocked (bs > 1) function uses its own parameters. */
+typedef enum cq_fn {
+  CQ_FN_COEF = 0,    /* sum_k w[k*bs + a] psi_k(xi)                                             */
+  CQ_FN_CONST = 1,   /* p[a]                                              (1 parameter / comp.) */
+  CQ_FN_AFFINE = 2,  /* p[4a] + p[4a+1] x + p[4a+2] y + p[4a+3] z         (4 parameters / comp.) */
+  CQ_FN_SINPROD = 3  /* p[a] * prod_d sin(pi x_d)   demo/poisson.py:59-67 (1 parameter / comp.) */
+} cq_fn;
+
+/* basix::cell::type values used by the reference (call_basix.h:61,68; README.md:153) */
+#define CQ_CELL_QUADRILATERAL 4
+#define CQ_CELL_HEXAHEDRON 5
+
+#define CQ_MAX_CONSTS 16
+
+/* Form descriptor.  consts is a HOST pointer (copied into the launch parameters):
+ *   Nitsche forms: consts[0] = betaN, function parameters p = consts + 1;
+ *   all other forms: p = consts.
+ * For L2_ERR / H10_ERR the coefficient is uh (always CQ_FN_COEF) and fn_kind describes u_ex. */
+typedef struct cq_form_desc {
+  int32_t form;       /* cq_form */
+  int32_t cell_type;  /* CQ_CELL_QUADRILATERAL | CQ_CELL_HEXAHEDRON */
+  int32_t degree;     /* 1 | 2 : Lagrange degree of the form's space (call_basix.h:63-73) */
+  int32_t bs;         /* block size of the space: 1, or gdim for VectorFunctionSpace (utils.py:47-62) */
+  int32_t fn_kind;    /* cq_fn */
+  int32_t nconsts;    /* <= CQ_MAX_CONSTS */
+  const double* consts;
+} cq_form_desc;
+
+/* Mesh geometry exactly as utils.get_vertices returns it (utils.py:66-71):
+ *   geom_dofmap [num_cells, nv] int32 row-major, nv = 4 (quad) | 8 (hex), dolfinx local order
+ *   coords      [num_nodes, 3]  f64 row-major (z = 0 in 2-D)                                  */
+typedef struct cq_mesh {
+  int64_t num_cells;
+  int64_t num_nodes;
+  const int32_t* geom_dofmap;
+  const double* coords;
+} cq_mesh;
+
+/* Function-space data as utils.get_dofs returns it (utils.py:33-63), kept un-expanded:
+ *   dofmap [num_cells, n] int32, n = (degree+1)^gdim scalar dofs per cell; the blocked index
+ *   of component a of local dof i is dofmap[c, i]*bs + a (utils.py:59-62).
+ *   coeffs [num_cells, n*bs] f64, packed coefficient of the form, indexed by MESH cell id
+ *   (assemble_matrix.py:92), or NULL when the form has none.                                  */
+typedef struct cq_space {
+  int64_t num_dofs;        /* scalar dofs; vector length = num_dofs * bs */
+  const int32_t* dofmap;
+  const double* coeffs;
+} cq_space;
+
+/* One qr_data tuple (cells, qr_pts, qr_w[, qr_n]) (assemble_matrix.py:65-73) in ragged
+ * CSR form: entry k of the list integrates mesh cell cells[k] with the points
+ * offsets[k] .. offsets[k+1]-1.
+ *   pts     [num_points, gdim] f64, point-major interleaved reference coordinates (call_basix.h:38-39)
+ *   weights [num_points]       f64, reference-measure weights (kernel multiplies by |det J|)
+ *   normals [num_points, gdim] f64 physical normals, or NULL for a 3-tuple                   */
+typedef struct cq_quadrature {
+  int64_t num_entries;
+  int64_t num_points;
+  const int32_t* cells;
+  const int64_t* offsets;  /* [num_entries + 1], offsets[0] = 0 */
+  const double* pts;
+  const double* weights;
+  const double* normals;
+} cq_quadrature;
+
+/* CSR matrix with the layout dolfinx.cpp.fem.petsc.create_matrix gives an AIJ Mat
+ * (assemble_matrix.py:19): rows = num_dofs*bs, columns ascending inside each row.            */
+typedef struct cq_csr {
+  int64_t num_rows;
+  int64_t nnz;
+  const int64_t* indptr;   /* [num_rows + 1] */
+  const int32_t* indices;  /* [nnz] */
+  double* values;          /* [nnz] -- accumulated into (ADD_VALUES); caller zeroes */
+} cq_csr;
+
+typedef struct cq_ctx cq_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int cq_abi_version(void);
+const char* cq_last_error(void);
+int cq_ctx_create(int device, cq_ctx** out);
+int cq_ctx_destroy(cq_ctx* ctx);
+/* Synchronises `stream` and returns CQ_ERR_SPARSITY if any launch since the last check hit a
+ * (row, col) missing from the pattern (the reference drops PETSc's return code,
+ * assemble_matrix.py:103; here it is reported). Resets the flag. */
+int cq_ctx_check(cq_ctx* ctx, void* stream);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t cq_ctx_launch_count(const cq_ctx* ctx);
+/* Kernel variant: 0 = auto, 1 = direct-load kernel, 2 = bulk-copy (TMA) staged persistent kernel. */
+int cq_ctx_set_variant(cq_ctx* ctx, int variant);
+
+/* ---- the hot path (device pointers) ---------------------------------------------------- */
+int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                       const cq_space* space, const cq_quadrature* qr, const cq_csr* A,
+                       void* stream);
+/* b [num_dofs*bs] f64, accumulated into: b[dofs[cell, j]] += b_local[j] (assemble_vector.py:93-94) */
+int cq_assemble_vector(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                       const cq_space* space, const cq_quadrature* qr, double* b, void* stream);
+/* m [1] f64 on the device, accumulated into: m[0] += m_local[0] (assemble_scalar.py:82).
+ * space may be NULL when the form has no coefficient. */
+int cq_assemble_scalar(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                       const cq_space* space, const cq_quadrature* qr, double* m, void* stream);
+
+/* ---- parity / debug hooks --------------------------------------------------------------- */
+/* call_basix for every point of `qr`: out [num_points, nbf] = D^alpha psi_j(xi_q) with
+ * basix_derivative 0 value, 1 d/dxi0, 2 d/dxi1, 3 d/dxi2 (call_basix.h:34-39,79-81). */
+int cq_tabulate(cq_ctx* ctx, int cell_type, int degree, int basix_derivative, int64_t num_points,
+                const double* pts, double* out, void* stream);
+/* Un-scattered element tensors: out [num_entries, len], len = (n*bs)^2 | n*bs | 1. */
+int cq_element_tensors(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                       const cq_space* space, const cq_quadrature* qr, double* out, void* stream);
+
+/* ---- multi-GPU receive side --------------------------------------------------------------- */
+/* values[indptr[row0] + i] += recv[i] for the nnz of rows [row0, row0 + nrows): adds a
+ * neighbour rank's contributions to rows this rank owns. */
+int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t nrows,
+                           const double* recv, void* stream);
+/* y[i] += x[i], i < n (vector interface dofs) */
+int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream);
+
+/* ---- end-to-end entry points (HOST pointers; copies are part of the call) ------------------
+ * The reference-facing call with host buffers: qr arrays, and the result, live in (ideally
+ * pinned) host memory; mesh/space/pattern are device-resident setup data like the PETSc Mat
+ * and dolfinx mesh are in the reference.  Points are streamed host->device in chunks that
+ * overlap with the kernel; the result is copied back before the call returns.              */
+int cq_assemble_matrix_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                            const cq_space* space, const cq_quadrature* qr_host, const cq_csr* A,
+                            double* values_host, void* stream);
+int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                            const cq_space* space, const cq_quadrature* qr_host, double* b_dev,
+                            double* b_host, void* stream);
+int cq_assemble_scalar_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
+                            const cq_space* space, const cq_quadrature* qr_host, double* m_host,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CQ_B200_H */

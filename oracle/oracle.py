@@ -1,0 +1,154 @@
+"""ctypes binding of the CPU oracle (oracle/cq_oracle.c).  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package (customquad_b200/) never does.
+
+The three entry points have the reference's signatures
+(reference customquad/assemble_matrix.py:10, assemble_vector.py:8, assemble_scalar.py:8):
+``assemble_*(form, qr_data)`` with ``qr_data`` a list with one tuple per cell integral, and
+follow the same host steps: get_dofs / get_vertices, pack coefficients and constants, create
+and zero the matrix, fetch the kernel, run assemble_cells.  Results are host objects
+(scipy CSR, numpy vector, float).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "cq_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "cq_b200.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        base = ["gcc", "-O2", "-fPIC", "-Wall", "-std=c11", "-D_GNU_SOURCE", "-shared", "-o", so, src, "-lm"]
+        r = subprocess.run(base[:1] + ["-fopenmp"] + base[1:], capture_output=True, text=True)
+        if r.returncode != 0:  # toolchain without libgomp: serial oracle
+            subprocess.run(base, check=True)
+    return so
+
+
+class _Args(C.Structure):
+    _fields_ = [
+        ("form", C.c_int), ("cell_type", C.c_int), ("degree", C.c_int), ("bs", C.c_int),
+        ("fn_kind", C.c_int), ("faithful", C.c_int), ("nthreads", C.c_int),
+        ("vertices", C.c_void_p), ("coords", C.c_void_p), ("dofmap", C.c_void_p),
+        ("coeffs", C.c_void_p), ("ncoef", C.c_int), ("consts", C.c_void_p),
+        ("num_entries", C.c_int64), ("cells", C.c_void_p), ("offsets", C.c_void_p),
+        ("pts", C.c_void_p), ("w", C.c_void_p), ("normals", C.c_void_p),
+    ]  # fmt: skip
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        for name in ("cq_oracle_assemble_matrix", "cq_oracle_assemble_vector", "cq_oracle_assemble_scalar", "cq_oracle_element_tensors"):
+            getattr(L, name).restype = C.c_int64
+        L.cq_oracle_tabulate.restype = C.c_int
+        L.cq_oracle_tabulate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def max_threads() -> int:
+    return int(lib().cq_oracle_max_threads())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _prepare(form, qr, nthreads, faithful):
+    """Host steps of the reference's assemble_* drivers (assemble_matrix.py:11-17)."""
+    from customquad_b200.quadrature import normalise_qr  # host-side data model only
+
+    mesh = form.mesh
+    gdim = mesh.geometry.dim
+    q = normalise_qr(qr, gdim)
+    keep = {}
+    keep["vertices"] = np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)  # utils.get_vertices
+    keep["coords"] = np.ascontiguousarray(mesh.geometry.x, dtype=np.float64)
+    V = form.function_spaces[0] if form.function_spaces else (form.coefficient.function_space if form.coefficient is not None else None)
+    keep["dofmap"] = None if V is None else np.ascontiguousarray(V.dofmap.list, dtype=np.int32)  # utils.get_dofs
+    coeffs = None if form.coefficient is None else np.ascontiguousarray(form.coefficient.packed())  # pack_coefficients
+    keep["coeffs"] = coeffs
+    consts = form.consts()  # pack_constants
+    keep["consts"] = consts if consts.size else np.zeros(1)
+    keep["q"] = q
+    a = _Args(
+        int(form.kind), int(mesh.cell_type), int(form.degree), int(form.bs), int(form.fn_kind), int(faithful), int(nthreads),
+        _ptr(keep["vertices"]), _ptr(keep["coords"]), _ptr(keep["dofmap"]),
+        _ptr(coeffs), 0 if coeffs is None else coeffs.shape[1], _ptr(keep["consts"]),
+        q.num_entries, _ptr(q.cells), _ptr(q.offsets), _ptr(q.pts), _ptr(q.w), _ptr(q.n),
+    )  # fmt: skip
+    if q.num_entries:
+        assert q.cells.min() >= 0 and q.cells.max() < mesh.num_cells, "cell index out of range"
+    return a, keep, V
+
+
+def assemble_matrix(form, qr_data, nthreads: int = 1, faithful: bool = False, pattern=None):
+    """reference customquad/assemble_matrix.py:10-47.  Returns scipy.sparse.csr_matrix whose
+    structure is the full form pattern (create_matrix(form), :19-20)."""
+    import scipy.sparse as sp
+    from customquad_b200.sparsity import build_pattern
+
+    assert form.rank == 2
+    V = form.function_spaces[0]
+    if pattern is None:
+        pattern = build_pattern(V.dofmap.list, V.dofmap.num_dofs, V.bs)
+    values = np.zeros(pattern.nnz)  # A.zeroEntries()
+    for i, _id in enumerate(form.integral_ids()):  # one qr tuple per integral, by position (:26,42)
+        a, keep, _ = _prepare(form, qr_data[i], nthreads, faithful)
+        missing = lib().cq_oracle_assemble_matrix(C.byref(a), _ptr(pattern.indptr), _ptr(pattern.indices), _ptr(values))
+        assert missing == 0, f"{missing} entries outside the sparsity pattern"
+    idx_t = np.int32 if pattern.nnz < 2**31 else np.int64
+    return sp.csr_matrix((values, pattern.indices, pattern.indptr.astype(idx_t)), shape=(pattern.num_rows, pattern.num_rows))
+
+
+def assemble_vector(form, qr_data, nthreads: int = 1, faithful: bool = False) -> np.ndarray:
+    """reference customquad/assemble_vector.py:8-49."""
+    assert form.rank == 1
+    V = form.function_spaces[0]
+    b = np.zeros(V.num_dofs)  # create_vector(index_map, bs) (:27)
+    for i, _id in enumerate(form.integral_ids()):
+        a, keep, _ = _prepare(form, qr_data[i], nthreads, faithful)
+        lib().cq_oracle_assemble_vector(C.byref(a), _ptr(b))
+    return b
+
+
+def assemble_scalar(form, qr_data, nthreads: int = 1, faithful: bool = False) -> float:
+    """reference customquad/assemble_scalar.py:8-34."""
+    assert form.rank == 0
+    m = np.zeros(1)
+    for i, _id in enumerate(form.integral_ids()):
+        a, keep, _ = _prepare(form, qr_data[i], nthreads, faithful)
+        lib().cq_oracle_assemble_scalar(C.byref(a), _ptr(m))
+    return float(m[0])
+
+
+def element_tensors(form, qr, nthreads: int = 1, faithful: bool = False) -> np.ndarray:
+    """Un-scattered element tensors [num_entries, len] (one generated-kernel call per entry)."""
+    a, keep, V = _prepare(form, qr, nthreads, faithful)
+    n = (form.degree + 1) ** form.mesh.geometry.dim * form.bs
+    ln = {2: n * n, 1: n, 0: 1}[form.rank]
+    out = np.zeros((keep["q"].num_entries, ln))
+    lib().cq_oracle_element_tensors(C.byref(a), form.rank, _ptr(out))
+    return out
+
+
+def tabulate(cell_type: int, degree: int, basix_derivative: int, pts: np.ndarray) -> np.ndarray:
+    """call_basix (reference customquad/call_basix.h:14-81) on [nq, gdim] points -> [nq, nbf]."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    nq, gdim = pts.shape
+    nbf = (degree + 1) ** gdim
+    out = np.zeros((nq, nbf))
+    r = lib().cq_oracle_tabulate(int(cell_type), degree, basix_derivative, nq, _ptr(pts), _ptr(out))
+    assert r == nbf
+    return out
