@@ -1,0 +1,109 @@
+"""ctypes binding of libcq_b200.so (include/cq_b200.h).  No CPU fallback: if the library is not
+built, or there is no CUDA device, the first assemble_* call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcq_b200.so")
+
+CQ_OK = 0
+CQ_ERR_SPARSITY = -4
+
+
+class FormDesc(C.Structure):
+    _fields_ = [("form", C.c_int32), ("cell_type", C.c_int32), ("degree", C.c_int32), ("bs", C.c_int32),
+                ("fn_kind", C.c_int32), ("nconsts", C.c_int32), ("consts", C.POINTER(C.c_double))]  # fmt: skip
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("num_cells", C.c_int64), ("num_nodes", C.c_int64), ("geom_dofmap", C.c_void_p), ("coords", C.c_void_p)]
+
+
+class SpaceDesc(C.Structure):
+    _fields_ = [("num_dofs", C.c_int64), ("dofmap", C.c_void_p), ("coeffs", C.c_void_p)]
+
+
+class QuadratureDesc(C.Structure):
+    _fields_ = [("num_entries", C.c_int64), ("num_points", C.c_int64), ("cells", C.c_void_p), ("offsets", C.c_void_p),
+                ("pts", C.c_void_p), ("weights", C.c_void_p), ("normals", C.c_void_p)]  # fmt: skip
+
+
+class CsrDesc(C.Structure):
+    _fields_ = [("num_rows", C.c_int64), ("nnz", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p)]
+
+
+class CqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libcq_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_ctx = {}
+_lock = threading.Lock()
+
+# every symbol include/cq_b200.h declares (tests check the exports against the header)
+_SIGNATURES = {
+    "cq_abi_version": (C.c_int, []),
+    "cq_last_error": (C.c_char_p, []),
+    "cq_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "cq_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "cq_ctx_check": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cq_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "cq_ctx_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "cq_assemble_matrix": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p]),
+    "cq_assemble_vector": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+    "cq_assemble_scalar": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+    "cq_tabulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_element_tensors": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+    "cq_csr_accumulate_rows": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cq_axpy": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_assemble_matrix_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
+    "cq_assemble_vector_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_assemble_scalar_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+}  # fmt: skip
+
+
+def load():
+    """dlopen the in-tree library and declare the signatures.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `python customquad_b200/build.py`); customquad_b200 has no CPU fallback"
+                    )
+                L = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return load().cq_last_error().decode()
+
+
+def check(rc: int):
+    if rc != CQ_OK:
+        raise CqError(rc, last_error())
+
+
+def ctx(device_index: int):
+    """One cq_ctx per device per process (one ctx per device, not re-entrant)."""
+    L = load()
+    if device_index not in _ctx:
+        h = C.c_void_p()
+        check(L.cq_ctx_create(int(device_index), C.byref(h)))
+        _ctx[device_index] = h
+    return _ctx[device_index]
+
+
+def launch_count(device_index: int = 0) -> int:
+    return int(load().cq_ctx_launch_count(ctx(device_index)))

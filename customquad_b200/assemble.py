@@ -1,3 +1,255 @@
-def assemble_matrix(form, qr_data):
-    raise NotImplementedError
-assemble_vector = assemble_scalar = assemble_matrix
+"""``assemble_matrix / assemble_vector / assemble_scalar(form, qr_data)``: the reference's three
+entry points (reference customquad/assemble_matrix.py:10-47, assemble_vector.py:8-49,
+assemble_scalar.py:8-34) with the cell loop, basix tabulation, generated kernel and
+MatSetValuesLocal replaced by one CUDA launch per cell integral through the C-ABI
+(include/cq_b200.h).  Host code only stages arrays; PyTorch is used for device buffers."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .forms import Form
+from .la import CSRMatrix, Vector
+from .quadrature import RaggedQuadrature, normalise_qr
+from .sparsity import build_pattern, build_pattern_torch
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("customquad_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _dev():
+    torch = _torch()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ---- device staging of the read-only inputs (cached on the host objects) ---------------------
+def mesh_on_device(mesh, dev):
+    """utils.get_vertices (utils.py:66-71) on the device."""
+    torch = _torch()
+    if dev not in mesh._dev:
+        mesh._dev[dev] = (
+            torch.from_numpy(np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)).to(dev),
+            torch.from_numpy(np.ascontiguousarray(mesh.geometry.x, dtype=np.float64)).to(dev),
+        )
+    return mesh._dev[dev]
+
+
+def space_on_device(V, dev):
+    """utils.get_dofs (utils.py:33-63), kept un-blocked."""
+    torch = _torch()
+    if dev not in V._dev:
+        V._dev[dev] = torch.from_numpy(np.ascontiguousarray(V.dofmap.list, dtype=np.int32)).to(dev)
+    return V._dev[dev]
+
+
+def pattern_on_device(V, dev, cells=None):
+    """dolfinx.cpp.fem.petsc.create_matrix(form) (assemble_matrix.py:19): the CSR structure."""
+    torch = _torch()
+    key = ("pattern", dev, None if cells is None else hash(np.asarray(cells).tobytes()))
+    if key not in V._dev:
+        d = V.dofmap.list
+        if cells is None and d.shape[0] * d.shape[1] ** 2 > 5e7:  # big mesh: build on the device
+            indptr, indices = build_pattern_torch(space_on_device(V, dev), V.dofmap.num_dofs, V.bs)
+        else:
+            p = build_pattern(d, V.dofmap.num_dofs, V.bs, cells)
+            indptr, indices = torch.from_numpy(p.indptr).to(dev), torch.from_numpy(p.indices).to(dev)
+        V._dev[key] = (indptr, indices)
+    return V._dev[key]
+
+
+def coefficient_on_device(f, dev):
+    """dolfinx.cpp.fem.pack_coefficients (assemble_matrix.py:16): [num_cells, n*bs]."""
+    torch = _torch()
+    V = f.function_space
+    d = space_on_device(V, dev).to(torch.int64)
+    arr = torch.from_numpy(f.array).to(dev)
+    if V.bs == 1:
+        return arr[d].contiguous()
+    idx = (d[:, :, None] * V.bs + torch.arange(V.bs, device=dev)[None, None, :]).reshape(d.shape[0], -1)
+    return arr[idx].contiguous()
+
+
+def qr_on_device(q: RaggedQuadrature, dev):
+    torch = _torch()
+    if dev not in q._dev:
+        up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        q._dev[dev] = (up(q.cells), up(q.offsets), up(q.pts), up(q.w), up(q.n))
+    return q._dev[dev]
+
+
+# ---- descriptors --------------------------------------------------------------------------------
+class _Call:
+    """Everything one C-ABI call needs, kept alive for the duration of the call."""
+
+    def __init__(self, form: Form, qr, dev, host_qr: bool = False):
+        mesh = form.mesh
+        gdim = mesh.geometry.dim
+        self.q = normalise_qr(qr, gdim)
+        q = self.q
+        if q.num_entries:
+            assert int(q.cells.min()) >= 0 and int(q.cells.max()) < mesh.num_cells, "cell index out of range"
+        if form.kind.name.startswith("NITSCHE"):
+            assert q.n is not None, "this form needs normals: pass (cells, qr_pts, qr_w, qr_n)"
+        self.keep = []
+        gd, xc = mesh_on_device(mesh, dev)
+        self.mesh = _lib.MeshDesc(mesh.num_cells, mesh.geometry.x.shape[0], _ptr(gd), _ptr(xc))
+        self.V = form.function_spaces[0] if form.function_spaces else (form.coefficient.function_space if form.coefficient is not None else None)
+        self.space = None
+        if self.V is not None:
+            dm = space_on_device(self.V, dev)
+            co = coefficient_on_device(form.coefficient, dev) if form.coefficient is not None else None
+            self.keep += [dm, co]
+            self.space = _lib.SpaceDesc(self.V.dofmap.num_dofs, _ptr(dm), _ptr(co))
+        consts = form.consts()
+        self._consts = (C.c_double * max(1, consts.size))(*consts.tolist())
+        self.form = _lib.FormDesc(int(form.kind), int(mesh.cell_type), int(form.degree), int(form.bs), int(form.fn_kind), int(consts.size), self._consts)
+        if host_qr:
+            arrs = (q.cells, q.offsets, q.pts, q.w, q.n)
+            hp = lambda a: None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())  # noqa: E731
+            self.keep += list(arrs)
+            self.qr = _lib.QuadratureDesc(q.num_entries, q.num_points, *[hp(a) for a in arrs])
+        else:
+            t = qr_on_device(q, dev)
+            self.keep += list(t)
+            self.qr = _lib.QuadratureDesc(q.num_entries, q.num_points, *[_ptr(a) for a in t])
+
+    def space_ref(self):
+        return None if self.space is None else C.byref(self.space)
+
+
+def create_matrix(form: Form, pattern_cells=None) -> CSRMatrix:
+    """Zeroed matrix on the form's pattern (create_matrix + zeroEntries, assemble_matrix.py:19-20)."""
+    torch = _torch()
+    dev = _dev()
+    V = form.function_spaces[0]
+    indptr, indices = pattern_on_device(V, dev, pattern_cells)
+    data = torch.zeros(indices.shape[0], dtype=torch.float64, device=dev)
+    n = V.num_dofs
+    return CSRMatrix(indptr, indices, data, (n, n), dev.index, _stream_ptr())
+
+
+def _csr_desc(A: CSRMatrix):
+    return _lib.CsrDesc(A.shape[0], A.nnz, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data))
+
+
+def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: str = "form") -> CSRMatrix:
+    """reference customquad/assemble_matrix.py:10-47.  Returns the (device) CSR matrix; like the
+    reference's PETSc Mat it is "unassembled" until ``A.assemble()``."""
+    assert form.rank == 2
+    L = _lib.load()
+    dev = _dev()
+    ctx = _lib.ctx(dev.index)
+    ids = form.integral_ids()
+    if A is None:
+        cells = None
+        if pattern == "cells":
+            cells = np.concatenate([np.asarray(normalise_qr(qr_data[i], form.mesh.geometry.dim).cells) for i in range(len(ids))])
+        A = create_matrix(form, cells)
+    csr = _csr_desc(A)
+    for i, _id in enumerate(ids):  # qr tuples are matched to integrals by position (:26,42)
+        c = _Call(form, qr_data[i], dev)
+        _lib.check(L.cq_assemble_matrix(ctx, C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), _stream_ptr()))
+    A.assembled = False
+    return A
+
+
+def assemble_vector(form: Form, qr_data, b: Vector | None = None) -> Vector:
+    """reference customquad/assemble_vector.py:8-49."""
+    assert form.rank == 1
+    torch = _torch()
+    L = _lib.load()
+    dev = _dev()
+    ctx = _lib.ctx(dev.index)
+    V = form.function_spaces[0]
+    if b is None:
+        b = Vector(torch.zeros(V.num_dofs, dtype=torch.float64, device=dev), dev.index)  # create_vector (:27)
+    for i, _id in enumerate(form.integral_ids()):
+        c = _Call(form, qr_data[i], dev)
+        _lib.check(L.cq_assemble_vector(ctx, C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), _ptr(b.data), _stream_ptr()))
+    return b
+
+
+def assemble_scalar(form: Form, qr_data) -> float:
+    """reference customquad/assemble_scalar.py:8-34: returns a Python float (no MPI reduction)."""
+    assert form.rank == 0
+    torch = _torch()
+    L = _lib.load()
+    dev = _dev()
+    ctx = _lib.ctx(dev.index)
+    m = torch.zeros(1, dtype=torch.float64, device=dev)
+    for i, _id in enumerate(form.integral_ids()):
+        c = _Call(form, qr_data[i], dev)
+        _lib.check(L.cq_assemble_scalar(ctx, C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), _ptr(m), _stream_ptr()))
+    return float(m.item())
+
+
+# ---- parity / debug hooks -------------------------------------------------------------------------
+def element_tensors(form: Form, qr) -> np.ndarray:
+    """Un-scattered element tensors [num_entries, len] (cq_element_tensors)."""
+    torch = _torch()
+    L = _lib.load()
+    dev = _dev()
+    c = _Call(form, qr, dev)
+    n = (form.degree + 1) ** form.mesh.geometry.dim * form.bs
+    ln = {2: n * n, 1: n, 0: 1}[form.rank]
+    out = torch.zeros((c.q.num_entries, ln), dtype=torch.float64, device=dev)
+    _lib.check(L.cq_element_tensors(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), _ptr(out), _stream_ptr()))
+    return out.cpu().numpy()
+
+
+def tabulate(cell_type: int, degree: int, basix_derivative: int, pts: np.ndarray) -> np.ndarray:
+    """call_basix on the device (cq_tabulate): [nq, gdim] points -> [nq, nbf]."""
+    torch = _torch()
+    L = _lib.load()
+    dev = _dev()
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    nq, gdim = pts.shape
+    p = torch.from_numpy(pts).to(dev)
+    out = torch.zeros((nq, (degree + 1) ** gdim), dtype=torch.float64, device=dev)
+    _lib.check(L.cq_tabulate(_lib.ctx(dev.index), int(cell_type), int(degree), int(basix_derivative), nq, _ptr(p), _ptr(out), _stream_ptr()))
+    return out.cpu().numpy()
+
+
+# ---- end-to-end (host buffer) calls -----------------------------------------------------------------
+def assemble_matrix_host(form: Form, q: RaggedQuadrature, A: CSRMatrix, values_host) -> None:
+    """cq_assemble_matrix_host: qr arrays and the result live in host (pinned) memory; the copies
+    are part of the call.  ``q`` holds numpy arrays or pinned torch CPU tensors; ``values_host``
+    is a float64 host buffer of A.nnz entries."""
+    L = _lib.load()
+    dev = _dev()
+    c = _Call(form, q, dev, host_qr=True)
+    csr = _csr_desc(A)
+    vh = C.c_void_p(values_host.ctypes.data if isinstance(values_host, np.ndarray) else values_host.data_ptr())
+    _lib.check(L.cq_assemble_matrix_host(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), vh, _stream_ptr()))
+
+
+def assemble_vector_host(form: Form, q: RaggedQuadrature, b: Vector, b_host) -> None:
+    L = _lib.load()
+    dev = _dev()
+    c = _Call(form, q, dev, host_qr=True)
+    bh = C.c_void_p(b_host.ctypes.data if isinstance(b_host, np.ndarray) else b_host.data_ptr())
+    _lib.check(L.cq_assemble_vector_host(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), _ptr(b.data), bh, _stream_ptr()))
+
+
+def assemble_scalar_host(form: Form, q: RaggedQuadrature) -> float:
+    L = _lib.load()
+    dev = _dev()
+    c = _Call(form, q, dev, host_qr=True)
+    m = np.zeros(1)
+    _lib.check(L.cq_assemble_scalar_host(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.c_void_p(m.ctypes.data), _stream_ptr()))
+    return float(m[0])

@@ -1,0 +1,394 @@
+// cq_api.cu -- the C-ABI of libcq_b200.so (include/cq_b200.h): argument checking, context,
+// parameter packing, and the host-buffer (end-to-end) entry points.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "cq_internal.h"
+
+namespace cq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return CQ_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return CQ_ERR_CUDA;
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+static int gdim_of(int cell_type) { return cell_type == CQ_CELL_QUADRILATERAL ? 2 : 3; }
+
+static int rank_of(int form) { return form < 10 ? 2 : (form < 20 ? 1 : 0); }
+
+// Validates the descriptor and packs what the kernels need.
+static int pack(cq_ctx* ctx, const cq_form_desc* f, const cq_mesh* mesh, const cq_space* space, const cq_quadrature* qr,
+                KParams& P) {
+  if (!ctx || !f || !mesh || !qr) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (f->cell_type != CQ_CELL_QUADRILATERAL && f->cell_type != CQ_CELL_HEXAHEDRON) {
+    // the reference's permutation table has no entry for other cells (call_basix.h:60-76)
+    set_error("cell_type %d unsupported: only quadrilateral (4) and hexahedron (5)", f->cell_type);
+    return CQ_ERR_UNSUPPORTED;
+  }
+  if (f->degree != 1 && f->degree != 2) { set_error("degree %d unsupported: only 1 and 2 (call_basix.h:63-73)", f->degree); return CQ_ERR_UNSUPPORTED; }
+  if (f->bs < 1 || f->bs > 3) { set_error("bs %d unsupported", f->bs); return CQ_ERR_UNSUPPORTED; }
+  if (f->nconsts < 0 || f->nconsts > CQ_MAX_CONSTS || (f->nconsts > 0 && !f->consts)) { set_error("bad consts"); return CQ_ERR_INVALID; }
+  const int rank = rank_of(f->form);
+  const int gdim = gdim_of(f->cell_type);
+  const bool nitsche = f->form == CQ_FORM_NITSCHE || f->form == CQ_FORM_NITSCHE_RHS;
+  const bool need_coef = rank < 2 && (f->fn_kind == CQ_FN_COEF || f->form == CQ_FORM_L2_ERR || f->form == CQ_FORM_H10_ERR);
+  if (qr->num_entries < 0 || qr->num_points < 0) { set_error("negative sizes"); return CQ_ERR_INVALID; }
+  if (qr->num_entries > 0 && (!qr->cells || !qr->offsets)) { set_error("qr.cells / qr.offsets null"); return CQ_ERR_INVALID; }
+  if (qr->num_points > 0 && (!qr->pts || !qr->weights)) { set_error("qr.pts / qr.weights null"); return CQ_ERR_INVALID; }
+  if (nitsche && qr->num_points > 0 && !qr->normals) { set_error("this form needs quadrature normals (a 4-tuple qr)"); return CQ_ERR_INVALID; }
+  if (!mesh->geom_dofmap || !mesh->coords) { set_error("mesh arrays null"); return CQ_ERR_INVALID; }
+  if ((rank >= 1 || need_coef) && (!space || !space->dofmap)) { set_error("space / dofmap null"); return CQ_ERR_INVALID; }
+  if (need_coef && !space->coeffs) { set_error("form needs a packed coefficient (space.coeffs)"); return CQ_ERR_INVALID; }
+  // vectorised loads: 16 B for 2-D point/normal pairs and the geometry dofmap, 8 B elsewhere
+  if (!aligned(mesh->geom_dofmap, 16) || (gdim == 2 && (!aligned(qr->pts, 16) || !aligned(qr->normals, 16))) ||
+      !aligned(qr->pts, 8) || !aligned(qr->weights, 8) || !aligned(qr->offsets, 8) || !aligned(mesh->coords, 8)) {
+    set_error("alignment: geom_dofmap and 2-D pts/normals need 16 B, f64/i64 arrays 8 B");
+    return CQ_ERR_ALIGN;
+  }
+  memset(&P, 0, sizeof P);
+  P.num_entries = qr->num_entries;
+  P.cells = qr->cells; P.offsets = qr->offsets; P.pts = qr->pts; P.w = qr->weights; P.normals = qr->normals;
+  P.geom_dofmap = mesh->geom_dofmap; P.coords = mesh->coords;
+  P.dofmap = space ? space->dofmap : nullptr;
+  P.coeffs = space ? space->coeffs : nullptr;
+  P.err_flag = ctx->err_flag;
+  P.bs = f->bs;
+  for (int i = 0; i < f->nconsts; ++i) P.p[i] = f->consts[i];
+  P.betaN = nitsche ? (f->nconsts > 0 ? f->consts[0] : 0.0) : 0.0;
+  if (nitsche && f->nconsts < 1) { set_error("Nitsche forms need consts[0] = betaN"); return CQ_ERR_INVALID; }
+  return CQ_OK;
+}
+
+static int set_device(cq_ctx* ctx) { return check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice"); }
+
+__global__ void accumulate_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
+}
+
+// call_basix on the device: one thread per (point, dof)
+template <int DIM, int DEG>
+__global__ void tabulate_kernel(const double* __restrict__ pts, int64_t nq, int deriv, double* __restrict__ out) {
+  constexpr int N = Lattice<DIM, DEG>::N;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    double xi[DIM], psi[N], g[N][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) xi[d] = pts[DIM * q + d];
+    tabulate_point<DIM, DEG, true, true>(xi, psi, g);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double v = psi[j];
+#pragma unroll
+      for (int e = 0; e < DIM; ++e)
+        if (deriv == e + 1) v = g[j][e];
+      out[q * N + j] = v;
+    }
+  }
+}
+
+}  // namespace cq
+
+using namespace cq;
+
+extern "C" {
+
+int cq_abi_version(void) { return CQ_B200_ABI_VERSION; }
+
+const char* cq_last_error(void) { return g_err; }
+
+int cq_ctx_create(int device, cq_ctx** out) {
+  if (!out) { set_error("null out"); return CQ_ERR_INVALID; }
+  *out = nullptr;
+  int n = 0;
+  if (int rc = check_cuda(cudaGetDeviceCount(&n), "cudaGetDeviceCount")) return rc;
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return CQ_ERR_INVALID; }
+  if (int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return rc;
+  cudaDeviceProp prop;
+  if (int rc = check_cuda(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return rc;
+  if (prop.major != 10) { set_error("libcq_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor); return CQ_ERR_UNSUPPORTED; }
+  cq_ctx* c = new (std::nothrow) cq_ctx();
+  if (!c) { set_error("out of host memory"); return CQ_ERR_INVALID; }
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  int rc = check_cuda(cudaMalloc(&c->err_flag, sizeof(int)), "cudaMalloc(err_flag)");
+  if (!rc) rc = check_cuda(cudaMemset(c->err_flag, 0, sizeof(int)), "cudaMemset(err_flag)");
+  if (!rc) rc = check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (int i = 0; i < 8 && !rc; ++i) rc = check_cuda(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming), "cudaEventCreate");
+  if (!rc) rc = check_cuda(cudaHostAlloc(&c->host_flag, sizeof(int), cudaHostAllocDefault), "cudaHostAlloc");
+  if (rc) { cq_ctx_destroy(c); return rc; }
+  *out = c;
+  return CQ_OK;
+}
+
+int cq_ctx_destroy(cq_ctx* ctx) {
+  if (!ctx) return CQ_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->err_flag) cudaFree(ctx->err_flag);
+  if (ctx->stage) cudaFree(ctx->stage);
+  if (ctx->scalar_dev) cudaFree(ctx->scalar_dev);
+  if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return CQ_OK;
+}
+
+int cq_ctx_check(cq_ctx* ctx, void* stream) {
+  if (!ctx) { set_error("null ctx"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "err_flag D2H")) return rc;
+  if (int rc = check_cuda(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s), "err_flag reset")) return rc;
+  if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
+  if (*ctx->host_flag) {
+    set_error("a cell produced a (row, col) pair that is absent from the CSR sparsity pattern");
+    return CQ_ERR_SPARSITY;
+  }
+  return CQ_OK;
+}
+
+int64_t cq_ctx_launch_count(const cq_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int cq_ctx_set_variant(cq_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 2) { set_error("bad variant"); return CQ_ERR_INVALID; }
+  ctx->variant = variant;
+  return CQ_OK;
+}
+
+int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                       const cq_quadrature* qr, const cq_csr* A, void* stream) {
+  KParams P;
+  if (int rc = pack(ctx, form, mesh, space, qr, P)) return rc;
+  if (rank_of(form->form) != 2) { set_error("form %d is not a bilinear form", form->form); return CQ_ERR_INVALID; }
+  if (!A || !A->indptr || !A->indices || !A->values) { set_error("CSR arrays null"); return CQ_ERR_INVALID; }
+  if (A->num_rows != space->num_dofs * form->bs) { set_error("CSR rows %lld != num_dofs*bs %lld", (long long)A->num_rows, (long long)(space->num_dofs * form->bs)); return CQ_ERR_INVALID; }
+  if (qr->num_entries == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  P.indptr = A->indptr; P.indices = A->indices; P.values = A->values;
+  return launch_matrix(ctx, *form, P, static_cast<cudaStream_t>(stream));
+}
+
+int cq_assemble_vector(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                       const cq_quadrature* qr, double* b, void* stream) {
+  KParams P;
+  if (int rc = pack(ctx, form, mesh, space, qr, P)) return rc;
+  if (rank_of(form->form) != 1) { set_error("form %d is not a linear form", form->form); return CQ_ERR_INVALID; }
+  if (!b) { set_error("b null"); return CQ_ERR_INVALID; }
+  if (qr->num_entries == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  P.out = b;
+  return launch_vector(ctx, *form, P, static_cast<cudaStream_t>(stream));
+}
+
+int cq_assemble_scalar(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                       const cq_quadrature* qr, double* m, void* stream) {
+  KParams P;
+  if (int rc = pack(ctx, form, mesh, space, qr, P)) return rc;
+  if (rank_of(form->form) != 0) { set_error("form %d is not a functional", form->form); return CQ_ERR_INVALID; }
+  if (!m) { set_error("m null"); return CQ_ERR_INVALID; }
+  if (qr->num_entries == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  P.out = m;
+  return launch_scalar(ctx, *form, P, static_cast<cudaStream_t>(stream));
+}
+
+int cq_element_tensors(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                       const cq_quadrature* qr, double* out, void* stream) {
+  KParams P;
+  if (int rc = pack(ctx, form, mesh, space, qr, P)) return rc;
+  if (!out) { set_error("out null"); return CQ_ERR_INVALID; }
+  if (qr->num_entries == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  P.out = out;
+  P.elem_out = 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (rank_of(form->form)) {
+    case 2: return launch_matrix(ctx, *form, P, s);
+    case 1: return launch_vector(ctx, *form, P, s);
+    default: return launch_scalar(ctx, *form, P, s);
+  }
+}
+
+int cq_tabulate(cq_ctx* ctx, int cell_type, int degree, int basix_derivative, int64_t num_points, const double* pts,
+                double* out, void* stream) {
+  if (!ctx || (num_points > 0 && (!pts || !out))) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if ((cell_type != CQ_CELL_QUADRILATERAL && cell_type != CQ_CELL_HEXAHEDRON) || (degree != 1 && degree != 2)) {
+    set_error("call_basix: no permutation for cell_type %d degree %d (call_basix.h:60-76)", cell_type, degree);
+    return CQ_ERR_UNSUPPORTED;
+  }
+  const int gdim = gdim_of(cell_type);
+  if (basix_derivative < 0 || basix_derivative > gdim) { set_error("basix_derivative %d out of range", basix_derivative); return CQ_ERR_INVALID; }
+  if (num_points == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = 128;
+  const int grid = (int)((num_points + threads - 1) / threads < 65535 ? (num_points + threads - 1) / threads : 65535);
+  if (gdim == 2 && degree == 1) tabulate_kernel<2, 1><<<grid, threads, 0, s>>>(pts, num_points, basix_derivative, out);
+  else if (gdim == 2) tabulate_kernel<2, 2><<<grid, threads, 0, s>>>(pts, num_points, basix_derivative, out);
+  else if (degree == 1) tabulate_kernel<3, 1><<<grid, threads, 0, s>>>(pts, num_points, basix_derivative, out);
+  else tabulate_kernel<3, 2><<<grid, threads, 0, s>>>(pts, num_points, basix_derivative, out);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "tabulate_kernel launch");
+}
+
+int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t nrows, const double* recv, void* stream) {
+  if (!ctx || !A || !A->indptr || !A->values || (!recv && nrows > 0)) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (row0 < 0 || nrows < 0 || row0 + nrows > A->num_rows) { set_error("row range out of bounds"); return CQ_ERR_INVALID; }
+  if (nrows == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the row range is contiguous in CSR storage: [indptr[row0], indptr[row0+nrows])
+  int64_t range[2];
+  if (int rc = check_cuda(cudaMemcpyAsync(&range[0], A->indptr + row0, sizeof(int64_t), cudaMemcpyDeviceToHost, s), "indptr D2H")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(&range[1], A->indptr + row0 + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s), "indptr D2H")) return rc;
+  if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
+  const int64_t n = range[1] - range[0];
+  if (n <= 0) return CQ_OK;
+  const int grid = (int)((n + 255) / 256 < (int64_t)ctx->num_sms * 8 ? (n + 255) / 256 : (int64_t)ctx->num_sms * 8);
+  accumulate_kernel<<<grid, 256, 0, s>>>(A->values + range[0], recv, n);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+}
+
+int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream) {
+  if (!ctx || (n > 0 && (!x || !y))) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (n <= 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  const int grid = (int)((n + 255) / 256 < (int64_t)ctx->num_sms * 8 ? (n + 255) / 256 : (int64_t)ctx->num_sms * 8);
+  accumulate_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, n);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// End-to-end entry points: qr data in host memory.  The ragged arrays are streamed to the device
+// in chunks of entries on ctx->copy_stream; the kernel for chunk c runs on `stream` as soon as its
+// copy has landed, overlapping with the copy of chunk c+1.  Because every kernel accumulates into
+// the same sink (ADD_VALUES), chunking does not change the result.
+// ---------------------------------------------------------------------------------------------
+static int ensure_stage(cq_ctx* ctx, size_t bytes) {
+  if (ctx->stage_bytes >= bytes) return CQ_OK;
+  if (ctx->stage) cudaFree(ctx->stage);
+  ctx->stage = nullptr;
+  ctx->stage_bytes = 0;
+  if (int rc = check_cuda(cudaMalloc(&ctx->stage, bytes), "cudaMalloc(stage)")) return rc;
+  ctx->stage_bytes = bytes;
+  return CQ_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <class LaunchFn>
+static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_quadrature* qh, cudaStream_t s, LaunchFn&& launch) {
+  if (!ctx || !form || !qh) { set_error("null argument"); return CQ_ERR_INVALID; }
+  const int gdim = gdim_of(form->cell_type);
+  const int64_t C = qh->num_entries, Pn = qh->num_points;
+  if (C == 0) return CQ_OK;
+  if (!qh->cells || !qh->offsets || (Pn > 0 && (!qh->pts || !qh->weights))) { set_error("qr host arrays null"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  // device layout inside the staging buffer (256-B aligned sub-arrays)
+  const size_t o_cells = 0;
+  const size_t o_off = align_up(o_cells + sizeof(int32_t) * C, 256);
+  const size_t o_pts = align_up(o_off + sizeof(int64_t) * (C + 1), 256);
+  const size_t o_w = align_up(o_pts + sizeof(double) * gdim * Pn, 256);
+  const size_t o_n = align_up(o_w + sizeof(double) * Pn, 256);
+  const size_t total = align_up(o_n + (qh->normals ? sizeof(double) * gdim * Pn : 0), 256);
+  if (int rc = ensure_stage(ctx, total)) return rc;
+  char* base = static_cast<char*>(ctx->stage);
+  cq_quadrature qd = *qh;
+  qd.cells = reinterpret_cast<int32_t*>(base + o_cells);
+  qd.offsets = reinterpret_cast<int64_t*>(base + o_off);
+  qd.pts = reinterpret_cast<double*>(base + o_pts);
+  qd.weights = reinterpret_cast<double*>(base + o_w);
+  qd.normals = qh->normals ? reinterpret_cast<double*>(base + o_n) : nullptr;
+
+  // copy stream must not start before prior work on `s` that may still read the staging buffer
+  if (int rc = check_cuda(cudaEventRecord(ctx->ev[7], s), "cudaEventRecord")) return rc;
+  if (int rc = check_cuda(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[7], 0), "cudaStreamWaitEvent")) return rc;
+
+  const int nchunks = C >= (1 << 16) ? 6 : 1;
+  for (int c = 0; c < nchunks; ++c) {
+    const int64_t k0 = C * c / nchunks, k1 = C * (c + 1) / nchunks;
+    if (k1 == k0) continue;
+    const int64_t p0 = qh->offsets[k0], p1 = qh->offsets[k1];
+    cudaStream_t cs = ctx->copy_stream;
+    int rc = check_cuda(cudaMemcpyAsync(const_cast<int32_t*>(qd.cells) + k0, qh->cells + k0, sizeof(int32_t) * (k1 - k0), cudaMemcpyHostToDevice, cs), "H2D cells");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(const_cast<int64_t*>(qd.offsets) + k0, qh->offsets + k0, sizeof(int64_t) * (k1 - k0 + 1), cudaMemcpyHostToDevice, cs), "H2D offsets");
+    if (!rc && p1 > p0) {
+      rc = check_cuda(cudaMemcpyAsync(const_cast<double*>(qd.pts) + gdim * p0, qh->pts + gdim * p0, sizeof(double) * gdim * (p1 - p0), cudaMemcpyHostToDevice, cs), "H2D pts");
+      if (!rc) rc = check_cuda(cudaMemcpyAsync(const_cast<double*>(qd.weights) + p0, qh->weights + p0, sizeof(double) * (p1 - p0), cudaMemcpyHostToDevice, cs), "H2D weights");
+      if (!rc && qh->normals)
+        rc = check_cuda(cudaMemcpyAsync(const_cast<double*>(qd.normals) + gdim * p0, qh->normals + gdim * p0, sizeof(double) * gdim * (p1 - p0), cudaMemcpyHostToDevice, cs), "H2D normals");
+    }
+    if (!rc) rc = check_cuda(cudaEventRecord(ctx->ev[c], cs), "cudaEventRecord");
+    if (!rc) rc = check_cuda(cudaStreamWaitEvent(s, ctx->ev[c], 0), "cudaStreamWaitEvent");
+    if (rc) return rc;
+    cq_quadrature qc = qd;
+    qc.cells = qd.cells + k0;
+    qc.offsets = qd.offsets + k0;
+    qc.num_entries = k1 - k0;
+    if (int lrc = launch(qc)) return lrc;
+  }
+  return CQ_OK;
+}
+
+extern "C" {
+
+int cq_assemble_matrix_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                            const cq_quadrature* qr_host, const cq_csr* A, double* values_host, void* stream) {
+  if (!A || !A->values) { set_error("CSR null"); return CQ_ERR_INVALID; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ctx) cudaSetDevice(ctx->device);
+  if (int rc = check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * A->nnz, s), "zeroEntries")) return rc;  // A.zeroEntries()
+  int rc = run_host_chunked(ctx, form, qr_host, s, [&](const cq_quadrature& qc) { return cq_assemble_matrix(ctx, form, mesh, space, &qc, A, stream); });
+  if (rc) return rc;
+  if (values_host)
+    if (int rc2 = check_cuda(cudaMemcpyAsync(values_host, A->values, sizeof(double) * A->nnz, cudaMemcpyDeviceToHost, s), "D2H values")) return rc2;
+  return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+}
+
+int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                            const cq_quadrature* qr_host, double* b_dev, double* b_host, void* stream) {
+  if (!b_dev || !space) { set_error("null argument"); return CQ_ERR_INVALID; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ctx) cudaSetDevice(ctx->device);
+  const size_t bytes = sizeof(double) * space->num_dofs * (form ? form->bs : 1);
+  if (int rc = check_cuda(cudaMemsetAsync(b_dev, 0, bytes, s), "zero b")) return rc;
+  int rc = run_host_chunked(ctx, form, qr_host, s, [&](const cq_quadrature& qc) { return cq_assemble_vector(ctx, form, mesh, space, &qc, b_dev, stream); });
+  if (rc) return rc;
+  if (b_host)
+    if (int rc2 = check_cuda(cudaMemcpyAsync(b_host, b_dev, bytes, cudaMemcpyDeviceToHost, s), "D2H b")) return rc2;
+  return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+}
+
+int cq_assemble_scalar_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                            const cq_quadrature* qr_host, double* m_host, void* stream) {
+  if (!ctx || !m_host) { set_error("null argument"); return CQ_ERR_INVALID; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaSetDevice(ctx->device);
+  if (!ctx->scalar_dev)
+    if (int rc = check_cuda(cudaMalloc(&ctx->scalar_dev, sizeof(double)), "cudaMalloc(m)")) return rc;
+  double* m_dev = ctx->scalar_dev;
+  if (int rc = check_cuda(cudaMemsetAsync(m_dev, 0, sizeof(double), s), "zero m")) return rc;
+  int rc = run_host_chunked(ctx, form, qr_host, s, [&](const cq_quadrature& qc) { return cq_assemble_scalar(ctx, form, mesh, space, &qc, m_dev, stream); });
+  if (rc) return rc;
+  if (int rc2 = check_cuda(cudaMemcpyAsync(m_host, m_dev, sizeof(double), cudaMemcpyDeviceToHost, s), "D2H m")) return rc2;
+  return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+}
+
+}  // extern "C"

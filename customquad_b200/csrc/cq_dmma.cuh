@@ -1,0 +1,180 @@
+// cq_dmma.cuh -- Q2 hexahedron (27 dofs) matrix forms on the FP64 tensor-core path.
+//
+// The scalar element block is dense 27x27 and the contraction over the cell's points is a real
+// GEMM:  S = B^T diag(w |det J|) B  with B [(q,k), j] the pulled-back gradient table
+// (SURVEY.md 2.1, K2).  tcgen05 has no f64 kind, so this uses warp-level
+// mma.sync.aligned.m8n8k4.f64 (DMMA.8x8x4 in SASS).  One warp per qr entry; each k-step covers
+// 4 quadrature points.  Lane (g = lane>>2, t = lane&3) evaluates dofs {g, 8+g, 16+g, 24+g} at
+// point 4*step + t, which is exactly the A- and B-fragment layout of m8n8k4 -- no shared memory,
+// no shuffles.  The 27x27 block is padded to 32x32 = 4x4 tiles; only the 10 upper-triangular
+// tiles are accumulated (20 FP64 registers per lane).
+#pragma once
+#include "cq_kernels.cuh"
+
+namespace cq {
+
+// packed lattice coordinates of Lattice<3,2>: t0 | t1 << 2 | t2 << 4, 27 dofs padded to 32
+__device__ __constant__ uint8_t c_q2hex_lat[32] = {
+    0 | 0 << 2 | 0 << 4, 2 | 0 << 2 | 0 << 4, 0 | 2 << 2 | 0 << 4, 2 | 2 << 2 | 0 << 4,
+    0 | 0 << 2 | 2 << 4, 2 | 0 << 2 | 2 << 4, 0 | 2 << 2 | 2 << 4, 2 | 2 << 2 | 2 << 4,
+    1 | 0 << 2 | 0 << 4, 0 | 1 << 2 | 0 << 4, 0 | 0 << 2 | 1 << 4, 2 | 1 << 2 | 0 << 4,
+    2 | 0 << 2 | 1 << 4, 1 | 2 << 2 | 0 << 4, 0 | 2 << 2 | 1 << 4, 2 | 2 << 2 | 1 << 4,
+    1 | 0 << 2 | 2 << 4, 0 | 1 << 2 | 2 << 4, 2 | 1 << 2 | 2 << 4, 1 | 2 << 2 | 2 << 4,
+    1 | 1 << 2 | 0 << 4, 1 | 0 << 2 | 1 << 4, 0 | 1 << 2 | 1 << 4, 2 | 1 << 2 | 1 << 4,
+    1 | 2 << 2 | 1 << 4, 1 | 1 << 2 | 2 << 4, 1 | 1 << 2 | 1 << 4, 0, 0, 0, 0, 0};
+
+CQ_DEVINL void dmma_m8n8k4(double (&d)[2], const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
+CQ_DEVINL double sel3(const double (&v)[3], const int t) { return t == 0 ? v[0] : (t == 1 ? v[1] : v[2]); }
+
+template <int FORM, int THREADS>
+__global__ void __launch_bounds__(THREADS) assemble_q2hex_dmma_kernel(const KParams P) {
+  constexpr int N = 27;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t warp_id = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t num_warps = (int64_t)gridDim.x * (THREADS / 32);
+
+  int lat[4][3];
+  bool valid[4];
+#pragma unroll
+  for (int tile = 0; tile < 4; ++tile) {
+    const int j = 8 * tile + g;
+    const int pk = c_q2hex_lat[j];
+    lat[tile][0] = pk & 3; lat[tile][1] = (pk >> 2) & 3; lat[tile][2] = (pk >> 4) & 3;
+    valid[tile] = j < N;
+  }
+
+  for (int64_t k = warp_id; k < P.num_entries; k += num_warps) {
+    const int32_t cell = __ldg(P.cells + k);
+    const int64_t q0 = __ldg(P.offsets + k), q1 = __ldg(P.offsets + k + 1);
+    double X[8][3];
+    load_cell_vertices<3>(P, cell, X);
+    CellGeom<3> geo;
+    geo.init(X, FORM == CQ_FORM_NITSCHE);
+    const double gamma = FORM == CQ_FORM_NITSCHE ? P.betaN / geo.hK : 0.0;
+
+    double D[10][2];  // upper-triangular tiles (ti <= tj), row-major enumeration
+#pragma unroll
+    for (int i = 0; i < 10; ++i) D[i][0] = D[i][1] = 0.0;
+
+    for (int64_t qb = q0; qb < q1; qb += 4) {
+      const int64_t q = qb + t;
+      const bool live = q < q1;
+      double xi[3] = {0.5, 0.5, 0.5}, nrm[3] = {0.0, 0.0, 0.0}, w = 0.0;
+      if (live) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) xi[d] = __ldg(P.pts + 3 * q + d);
+        w = __ldg(P.w + q);
+        if constexpr (FORM == CQ_FORM_NITSCHE)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) nrm[d] = __ldg(P.normals + 3 * q + d);
+      }
+      const Basis1D<2> b0(xi[0]), b1(xi[1]), b2(xi[2]);
+      double J[3][3], adj[3][3];
+      geo.jacobian(xi, J);
+      const double det = det_adj<3>(J, adj);
+      const double adet = fabs(det);
+
+      if constexpr (FORM == CQ_FORM_MASS) {
+        const double s = w * adet;
+        double f[4], sf[4];
+#pragma unroll
+        for (int tile = 0; tile < 4; ++tile) {
+          const double v = sel3(b0.v, lat[tile][0]) * sel3(b1.v, lat[tile][1]) * sel3(b2.v, lat[tile][2]);
+          f[tile] = valid[tile] ? v : 0.0;
+          sf[tile] = s * f[tile];
+        }
+        int e = 0;
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+          for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], sf[ti], f[tj]);
+      } else if constexpr (FORM == CQ_FORM_STIFFNESS) {
+        const double sc = w / adet;
+        double f[4][3], sf[4][3];
+#pragma unroll
+        for (int tile = 0; tile < 4; ++tile) {
+          const double v0 = sel3(b0.v, lat[tile][0]), v1 = sel3(b1.v, lat[tile][1]), v2 = sel3(b2.v, lat[tile][2]);
+          const double d0 = sel3(b0.d, lat[tile][0]), d1 = sel3(b1.d, lat[tile][1]), d2 = sel3(b2.d, lat[tile][2]);
+          const double gr[3] = {d0 * v1 * v2, v0 * d1 * v2, v0 * v1 * d2};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double a = fma(adj[2][c], gr[2], fma(adj[1][c], gr[1], adj[0][c] * gr[0]));
+            f[tile][c] = valid[tile] ? a : 0.0;
+            sf[tile][c] = sc * f[tile][c];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          int e = 0;
+#pragma unroll
+          for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], sf[ti][c], f[tj][c]);
+        }
+      } else {  // CQ_FORM_NITSCHE:  psi_i u_j - e_i psi_j,  e = s dn,  u = s gamma psi - e
+        const double s = w * adet, sg = s * gamma, inv_det = 1.0 / det;
+        double m[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) m[e] = fma(adj[e][2], nrm[2], fma(adj[e][1], nrm[1], adj[e][0] * nrm[0])) * inv_det;
+        double psi[4], ev[4], uv[4];
+#pragma unroll
+        for (int tile = 0; tile < 4; ++tile) {
+          const double v0 = sel3(b0.v, lat[tile][0]), v1 = sel3(b1.v, lat[tile][1]), v2 = sel3(b2.v, lat[tile][2]);
+          const double d0 = sel3(b0.d, lat[tile][0]), d1 = sel3(b1.d, lat[tile][1]), d2 = sel3(b2.d, lat[tile][2]);
+          const double dn = fma(m[2], v0 * v1 * d2, fma(m[1], v0 * d1 * v2, m[0] * (d0 * v1 * v2)));
+          psi[tile] = valid[tile] ? v0 * v1 * v2 : 0.0;
+          ev[tile] = valid[tile] ? s * dn : 0.0;
+          uv[tile] = fma(sg, psi[tile], -ev[tile]);
+        }
+        int e = 0;
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+          for (int tj = ti; tj < 4; ++tj, ++e) {
+            dmma_m8n8k4(D[e], psi[ti], uv[tj]);
+            dmma_m8n8k4(D[e], -ev[ti], psi[tj]);
+          }
+      }
+    }
+
+    // ---- sink: lane holds D[ti][tj] at row 8*ti + g, cols 8*tj + 2*t + {0,1} -------------------
+    const int bs = P.bs;
+    const int nl = N * bs;
+    int e = 0;
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = ti; tj < 4; ++tj, ++e) {
+        const int i = 8 * ti + g;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = 8 * tj + 2 * t + c;
+          if (i < N && j < N) {
+            const double v = D[e][c];
+            if (P.elem_out) {
+              double* o = P.out + k * (int64_t)(nl * nl);
+              for (int a = 0; a < bs; ++a) {
+                o[(i * bs + a) * nl + j * bs + a] = v;
+                if (ti != tj) o[(j * bs + a) * nl + i * bs + a] = v;
+              }
+            } else {
+              const int32_t di = __ldg(P.dofmap + (int64_t)cell * N + i);
+              const int32_t dj = __ldg(P.dofmap + (int64_t)cell * N + j);
+              for (int a = 0; a < bs; ++a) {
+                csr_add(P, (int64_t)di * bs + a, dj * bs + a, v);
+                if (ti != tj) csr_add(P, (int64_t)dj * bs + a, di * bs + a, v);  // diagonal tiles are full
+              }
+            }
+          }
+        }
+      }
+  }
+}
+
+}  // namespace cq

@@ -1,0 +1,49 @@
+// cq_internal.h -- host-side internals shared by the translation units of libcq_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/cq_b200.h"
+#include "cq_kernels.cuh"
+
+struct cq_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int variant = 0;
+  int* err_flag = nullptr;  // device
+  std::atomic<int64_t> launches{0};
+  // end-to-end (host buffer) path: grow-only device staging + a copy stream
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  int* host_flag = nullptr;  // pinned
+  double* scalar_dev = nullptr;  // device accumulator of the host-buffer scalar path
+};
+
+namespace cq {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// launchers implemented in cq_launch_*.cu; return cq_status
+int launch_matrix(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s);
+int launch_vector(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s);
+int launch_scalar(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s);
+
+// grid size for a grid-strided kernel: enough blocks for the work, at most a full wave
+template <auto Kernel>
+int grid_for(cq_ctx* ctx, int threads, int64_t work_per_block_unit, int64_t units, size_t smem = 0) {
+  static thread_local int blocks_per_sm = 0;  // one per kernel instantiation
+  if (blocks_per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, Kernel, threads, smem) != cudaSuccess || blocks_per_sm < 1)
+      blocks_per_sm = 1;
+  }
+  const int64_t need = (units + work_per_block_unit - 1) / work_per_block_unit;
+  const int64_t full = (int64_t)ctx->num_sms * blocks_per_sm;
+  return (int)(need < 1 ? 1 : (need < full ? need : full));
+}
+
+}  // namespace cq

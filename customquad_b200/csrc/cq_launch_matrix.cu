@@ -1,0 +1,44 @@
+// cq_launch_matrix.cu -- instantiation + dispatch of the rank-2 (bilinear form) kernels
+#include "cq_dmma.cuh"
+#include "cq_internal.h"
+
+namespace cq {
+
+template <class T, int G>
+static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
+  constexpr int THREADS = 256;
+  constexpr int64_t ENTRIES_PER_BLOCK = (THREADS / 32) * (32 / G);
+  const int grid = grid_for<assemble_direct_kernel<T, G, THREADS>>(ctx, THREADS, ENTRIES_PER_BLOCK, P.num_entries);
+  assemble_direct_kernel<T, G, THREADS><<<grid, THREADS, 0, s>>>(P);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "assemble_direct_kernel launch");
+}
+
+template <int FORM>
+static int launch_dmma(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
+  constexpr int THREADS = 128;
+  const int grid = grid_for<assemble_q2hex_dmma_kernel<FORM, THREADS>>(ctx, THREADS, THREADS / 32, P.num_entries);
+  assemble_q2hex_dmma_kernel<FORM, THREADS><<<grid, THREADS, 0, s>>>(P);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "assemble_q2hex_dmma_kernel launch");
+}
+
+template <int FORM>
+static int launch_matrix_form(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s) {
+  const bool quad = f.cell_type == CQ_CELL_QUADRILATERAL;
+  if (quad && f.degree == 1) return launch_direct<FormTraits<FORM, 2, 1, 1, CQ_FN_CONST>, 8>(ctx, P, s);
+  if (quad && f.degree == 2) return launch_direct<FormTraits<FORM, 2, 2, 1, CQ_FN_CONST>, 8>(ctx, P, s);
+  if (!quad && f.degree == 1) return launch_direct<FormTraits<FORM, 3, 1, 1, CQ_FN_CONST>, 8>(ctx, P, s);
+  return launch_dmma<FORM>(ctx, P, s);
+}
+
+int launch_matrix(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s) {
+  switch (f.form) {
+    case CQ_FORM_MASS: return launch_matrix_form<CQ_FORM_MASS>(ctx, f, P, s);
+    case CQ_FORM_STIFFNESS: return launch_matrix_form<CQ_FORM_STIFFNESS>(ctx, f, P, s);
+    case CQ_FORM_NITSCHE: return launch_matrix_form<CQ_FORM_NITSCHE>(ctx, f, P, s);
+    default: set_error("form %d is not a bilinear form", f.form); return CQ_ERR_INVALID;
+  }
+}
+
+}  // namespace cq

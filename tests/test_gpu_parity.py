@@ -1,0 +1,244 @@
+"""CUDA path vs the CPU oracle on identical seeded inputs, through the public API -> C-ABI.
+
+Tolerance (BASELINE.json north_star: values within 1e-12 relative in FP64 given atomic
+reordering): ||D||_F <= 1e-12 ||ref||_F and max|D| <= 1e-12 max|ref|.
+Sparsity pattern (indptr, indices) bit-exact."""
+import numpy as np
+import pytest
+
+import customquad_b200 as cq
+from customquad_b200 import forms
+from customquad_b200.quadrature import synthetic_ragged
+from tests import refcases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def close(a, ref, rtol=RTOL):
+    a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    scale = np.max(np.abs(ref)) if ref.size else 0.0
+    if scale == 0.0:
+        return bool(np.all(a == 0.0))
+    return np.linalg.norm(a - ref) <= rtol * np.linalg.norm(ref) and np.max(np.abs(a - ref)) <= rtol * scale
+
+
+def make_mesh(tdim, distort, seed=7):
+    if tdim == 2:
+        mesh = cq.create_rectangle([[-1.11, -1.51], [1.55, 1.22]], [7, 5])  # demo/poisson.py:42-43
+    else:
+        mesh = cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [4, 3, 5])  # :48-49
+    if distort:  # non-affine cells: J varies inside the cell
+        rng = np.random.default_rng(seed)
+        h = mesh.h()
+        mesh.geometry.x[:, :tdim] += rng.uniform(-0.2, 0.2, size=(mesh.geometry.x.shape[0], tdim)) * h
+    return mesh
+
+
+def all_forms(V, rng):
+    """Every integrand of SURVEY.md 8a a-6 on the space V."""
+    mesh, bs, g = V.mesh, V.bs, V.mesh.geometry.dim
+    f = cq.Function(V)
+    f.array[:] = rng.uniform(-1, 1, size=V.num_dofs)
+    amp = [g * np.pi**2 * (1.0 + 0.5 * a) for a in range(bs)]
+    sinp = cq.Analytic.sinprod(*amp)
+    aff = cq.Analytic.affine_blocked([(0.3 + a, [2.0, 1.0, -0.7][:g]) for a in range(bs)])
+    const = cq.Analytic.const(*[1.0 + a for a in range(bs)])
+    out = {
+        "mass": forms.mass(V),
+        "stiffness": forms.stiffness(V),
+        "nitsche": forms.nitsche(V, 10.0),
+        "load_coef": forms.load(V, f),
+        "load_sinprod": forms.load(V, sinp),
+        "load_affine": forms.load(V, aff),
+        "load_const": forms.load(V, const),
+        "nitsche_rhs_coef": forms.nitsche_rhs(V, f, 10.0),
+        "nitsche_rhs_sinprod": forms.nitsche_rhs(V, sinp, 10.0),
+        "integral_sq_coef": forms.integral_sq(f),
+        "l2_err_sinprod": forms.l2_error(f, sinp),
+        "l2_err_affine": forms.l2_error(f, aff),
+        "h10_err_sinprod": forms.h10_error(f, sinp),
+        "h10_err_affine": forms.h10_error(f, aff),
+    }
+    if bs == 1:
+        out["integral_one"] = forms.integral(mesh, 1.0)
+        out["integral_affine"] = forms.integral(mesh, cq.Analytic.affine(0.0, [2.0, 1.0, 0.5][:g]))
+        out["integral_sinprod"] = forms.integral(mesh, cq.Analytic.sinprod(1.0))
+    return out
+
+
+SPACES = [(2, 1, 1), (2, 2, 1), (3, 1, 1), (3, 2, 1), (2, 1, 2), (2, 2, 2), (3, 1, 3), (3, 2, 3)]
+
+
+@pytest.mark.parametrize("cell_type,degree", [(4, 1), (4, 2), (5, 1), (5, 2)])
+def test_tabulate_matches_call_basix(cuda_backend, cell_type, degree):
+    from customquad_b200.assemble import tabulate
+    from oracle import oracle
+
+    gdim = 2 if cell_type == 4 else 3
+    pts = np.random.default_rng(3).random((257, gdim))
+    for deriv in range(gdim + 1):
+        dev = tabulate(cell_type, degree, deriv, pts)
+        ref = oracle.tabulate(cell_type, degree, deriv, pts)
+        assert np.max(np.abs(dev - ref)) <= 1e-14 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("tdim,degree,bs", SPACES)
+@pytest.mark.parametrize("distort", [False, True])
+def test_element_tensors_match_oracle(cuda_backend, tdim, degree, bs, distort):
+    """One generated-kernel call per cell (README.md:133-158), before any scatter."""
+    from customquad_b200.assemble import element_tensors
+    from oracle import oracle
+
+    rng = np.random.default_rng(11)
+    mesh = make_mesh(tdim, distort)
+    V = cq.FunctionSpace(mesh, ("Lagrange", degree)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", degree))
+    cells = rng.permutation(mesh.num_cells)[: max(3, mesh.num_cells // 2)]
+    qr = synthetic_ragged(cells, tdim, 1, 19, seed=5, normals=True)
+    for name, form in all_forms(V, rng).items():
+        dev = element_tensors(form, qr)
+        ref = oracle.element_tensors(form, qr)
+        assert dev.shape == ref.shape
+        assert close(dev, ref), f"{name}: max rel {np.max(np.abs(dev - ref)) / np.max(np.abs(ref)):.3e}"
+
+
+@pytest.mark.parametrize("tdim,degree,bs", SPACES)
+def test_assembly_matches_oracle(cuda_backend, oracle_backend, tdim, degree, bs):
+    """Full path: element kernels + scatter into CSR / vector / scalar, ragged rules, cell subset
+    with repeats."""
+    rng = np.random.default_rng(23)
+    mesh = make_mesh(tdim, True)
+    V = cq.FunctionSpace(mesh, ("Lagrange", degree)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", degree))
+    cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 9)])
+    qr = synthetic_ragged(cells, tdim, 2, 33, seed=9, normals=True)
+    for name, form in all_forms(V, rng).items():
+        if form.rank == 2:
+            A, R = cuda_backend.matrix(form, [qr]), oracle_backend.matrix(form, [qr])
+            assert np.array_equal(A.indptr, R.indptr) and np.array_equal(A.indices, R.indices), name
+            assert close(A.data, R.data), f"{name}: {np.max(np.abs(A.data - R.data)) / np.max(np.abs(R.data)):.3e}"
+        elif form.rank == 1:
+            assert close(cuda_backend.vector(form, [qr]), oracle_backend.vector(form, [qr])), name
+        else:
+            m, r = cuda_backend.scalar(form, [qr]), oracle_backend.scalar(form, [qr])
+            assert abs(m - r) <= RTOL * abs(r), f"{name}: {m} vs {r}"
+
+
+# ---- the reference's own tests on the CUDA path -----------------------------------------------
+@pytest.mark.parametrize("idx", range(36))
+def test_reference_quads_hexes_assembly(cuda_backend, golden, idx):
+    refcases.assembly_case(cuda_backend, golden, idx)
+
+
+def test_reference_edges(cuda_backend, golden):
+    refcases.edges_case(cuda_backend, golden)
+
+
+def test_reference_edge_integral(cuda_backend, golden):
+    refcases.edge_integral_case(cuda_backend, golden)
+
+
+def test_reference_face_integral(cuda_backend, golden):
+    refcases.face_integral_case(cuda_backend, golden)
+
+
+def test_reference_volume(cuda_backend, golden):
+    refcases.volume_case(cuda_backend, golden)
+
+
+def test_reference_full_area(cuda_backend, golden):
+    refcases.full_area_case(cuda_backend, golden)
+
+
+# ---- input conventions and edge cases -----------------------------------------------------------
+def test_input_conventions(cuda_backend, oracle_backend):
+    """cells as list / int32 / int64, qr as list of flat arrays or 2-D arrays."""
+    mesh = make_mesh(2, False)
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    rng = np.random.default_rng(1)
+    cells = [3, 0, 7, 7, 12]
+    pts = [rng.random(2 * n) for n in (4, 1, 9, 2, 6)]
+    w = [rng.random(n) for n in (4, 1, 9, 2, 6)]
+    ref = oracle_backend.matrix(forms.stiffness(V), [(cells, pts, w)])
+    for c in (cells, np.array(cells, dtype=np.int32), np.array(cells, dtype=np.int64)):
+        A = cuda_backend.matrix(forms.stiffness(V), [(c, pts, w)])
+        assert close(A.data, ref.data)
+    P2 = rng.random((5, 6))
+    W2 = rng.random((5, 3))
+    A = cuda_backend.matrix(forms.mass(V), [(cells, P2, W2)])
+    assert close(A.data, oracle_backend.matrix(forms.mass(V), [(cells, P2, W2)]).data)
+
+
+def test_empty_and_degenerate(cuda_backend, oracle_backend):
+    mesh = make_mesh(2, False)
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    empty = (np.zeros(0, dtype=np.int32), [], [])
+    assert cuda_backend.matrix(forms.mass(V), [empty]).data.sum() == 0.0
+    assert np.all(cuda_backend.vector(forms.load(V, 1.0), [empty]) == 0.0)
+    assert cuda_backend.scalar(forms.integral(mesh, 1.0), [empty]) == 0.0
+    # entries with zero points among non-empty ones; one entry with a very long rule
+    rng = np.random.default_rng(2)
+    nq = [0, 5, 0, 3001, 1, 0]
+    cells = [1, 2, 3, 4, 5, 6]
+    pts = [rng.random(2 * n) for n in nq]
+    w = [rng.random(n) / max(n, 1) for n in nq]
+    for form in (forms.stiffness(V), forms.mass(V)):
+        A, R = cuda_backend.matrix(form, [(cells, pts, w)]), oracle_backend.matrix(form, [(cells, pts, w)])
+        assert close(A.data, R.data)
+    m = cuda_backend.scalar(forms.integral(mesh, 1.0), [(cells, pts, w)])
+    assert abs(m - oracle_backend.scalar(forms.integral(mesh, 1.0), [(cells, pts, w)])) <= RTOL * abs(m)
+
+
+def test_error_behaviour(cuda_backend):
+    """Same asserts as the reference (assemble_matrix.py:70-73) + loud failures."""
+    from customquad_b200._lib import CqError
+
+    mesh = make_mesh(2, False)
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    with pytest.raises(AssertionError):
+        cq.assemble_matrix(forms.mass(V), [([0, 1], [np.zeros(2)], [np.zeros(1), np.zeros(1)])])
+    with pytest.raises(AssertionError):
+        cq.assemble_matrix(forms.mass(V), [([0, 1], [np.zeros(2), np.zeros(2)], [np.zeros(1)])])
+    with pytest.raises(AssertionError):
+        cq.assemble_matrix(forms.nitsche(V, 10.0), [([0], [np.zeros(2)], [np.ones(1)])])  # no normals
+    # a cell outside the "cells" pattern is reported at assemble() (PETSc: new nonzero error)
+    A = cq.assemble.create_matrix(forms.mass(V), pattern_cells=[0, 1])
+    cq.assemble_matrix(forms.mass(V), [([mesh.num_cells - 1], [np.full(2, 0.5)], [np.ones(1)])], A=A)
+    with pytest.raises(CqError):
+        A.assemble()
+
+
+def test_pattern_builders_agree(cuda_backend):
+    import torch
+
+    from customquad_b200.sparsity import build_pattern, build_pattern_torch
+
+    for tdim, degree, bs in [(2, 2, 1), (3, 1, 3), (2, 1, 2)]:
+        mesh = make_mesh(tdim, False)
+        V = cq.FunctionSpace(mesh, ("Lagrange", degree), bs) if bs > 1 else cq.FunctionSpace(mesh, ("Lagrange", degree))
+        p = build_pattern(V.dofmap.list, V.dofmap.num_dofs, bs)
+        ip, ix = build_pattern_torch(torch.from_numpy(V.dofmap.list).cuda(), V.dofmap.num_dofs, bs, chunk_cells=7)
+        assert np.array_equal(ip.cpu().numpy(), p.indptr) and np.array_equal(ix.cpu().numpy(), p.indices)
+
+
+def test_host_buffer_entry_points(cuda_backend, oracle_backend):
+    """cq_assemble_*_host: qr and result in host memory, chunked copies inside the call."""
+    import torch
+
+    from customquad_b200 import assemble as asm
+
+    mesh = cq.create_rectangle([[0, 0], [1, 1]], [300, 300])  # > 2^16 entries => chunked path
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    qr = synthetic_ragged(np.arange(mesh.num_cells), 2, 1, 6, seed=4)
+    form = forms.stiffness(V)
+    A = asm.create_matrix(form)
+    vals = np.zeros(A.nnz)
+    asm.assemble_matrix_host(form, qr, A, vals)
+    R = oracle_backend.matrix(form, [qr])
+    assert close(vals, R.data)
+    b = cq.la.Vector(torch.zeros(V.num_dofs, dtype=torch.float64, device="cuda"), 0)
+    bh = np.zeros(V.num_dofs)
+    lf = forms.load(V, cq.Analytic.sinprod(2 * np.pi**2))
+    asm.assemble_vector_host(lf, qr, b, bh)
+    assert close(bh, oracle_backend.vector(lf, [qr]))
+    m = asm.assemble_scalar_host(forms.integral(mesh, 1.0), qr)
+    assert abs(m - oracle_backend.scalar(forms.integral(mesh, 1.0), [qr])) <= RTOL * abs(m)
