@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- runtime-quadrature assembly throughput on B200 (BASELINE.json metric).
+
+Workload at N=1 (BASELINE.json configs[1], SURVEY.md 8d "cfg 2"): 2-D Q1 and Q2 stiffness + mass
+matrices on a 2048x2048 quadrilateral mesh with synthetic ragged runtime quadrature, nq_c ~ U{16..64}
+points per cell, every cell listed.  One step = one pass of the hot path over that batch:
+four ``assemble_matrix`` calls (Q1 stiffness, Q1 mass, Q2 stiffness, Q2 mass), each zeroing its CSR
+values first as the reference does (assemble_matrix.py:19-20).
+
+    value = element tensors per second = 4 * num_cells / step time   (inputs resident in HBM)
+    e2e   = the same through cq_assemble_matrix_host: qr arrays in pinned host memory, H2D copies and
+            the D2H copy of the CSR values inside the timed region.
+
+N>1 (torchrun): the mesh grows with N (weak scaling): rank r owns the slab of 2048 cell-columns
+[r*2048, (r+1)*2048) of a (2048*N) x 2048 mesh, assembles into its own rows and ships the one
+interface dof line it does not own to rank r+1 over NCCL (customquad_b200/dist.py).
+
+``--impl reference`` times the CPU oracle (oracle/, the restatement of the reference's numba loop +
+generated kernel: the reference itself needs dolfinx/basix/ffcx/PETSc, absent here) with all host
+threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MESH_N = 2048
+NQ_LO, NQ_HI = 16, 64
+XMIN, XMAX = [-1.11, -1.51], [1.55, 1.22]  # demo/poisson.py:42-43
+FORMS = [("q1_stiffness", 1, "stiffness"), ("q1_mass", 1, "mass"), ("q2_stiffness", 2, "stiffness"), ("q2_mass", 2, "mass")]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}  # fmt: skip
+
+
+def algorithmic_bytes(num_cells, num_points, gdim, nv, n, num_nodes, nnz):
+    """per listed cell 4 (cell id) + 8 (int64 offset) + nq*8*(d+1) + 4*nv (geometry
+    dofmap) + 4*n (dofmap); + 24 per distinct geometry node; + 8*nnz output.  No credit for CSR
+    structure reads, atomics read-modify-write, or the memset."""
+    return num_cells * (4 + 8 + 4 * nv + 4 * n) + num_points * 8 * (gdim + 1) + 24 * num_nodes + 8 * nnz
+
+
+def build_problem(nx, ny, col0=0, total_nx=None):
+    """Mesh slab + spaces + synthetic ragged rule (SURVEY.md 8d generator, seed 20231)."""
+    import customquad_b200 as cq
+    from customquad_b200 import forms
+    from customquad_b200.quadrature import synthetic_ragged
+
+    total_nx = total_nx or nx
+    hx = (XMAX[0] - XMIN[0]) / MESH_N
+    mesh = cq.create_rectangle([[XMIN[0] + col0 * hx, XMIN[1]], [XMIN[0] + (col0 + nx) * hx, XMAX[1]]], [nx, ny])
+    spaces = {1: cq.FunctionSpace(mesh, ("Lagrange", 1)), 2: cq.FunctionSpace(mesh, ("Lagrange", 2))}
+    fl = [(name, getattr(forms, kind)(spaces[deg]), deg) for name, deg, kind in FORMS]
+    qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 2, NQ_LO, NQ_HI, seed=20231 + col0)
+    return mesh, spaces, fl, qr
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle on all host threads, a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from customquad_b200.sparsity import build_pattern
+
+    oracle.build()
+    threads = oracle.max_threads()
+    sample_cols = 192  # 192 x 2048 = 393,216 cells per step and form (~9% of the workload)
+    mesh, spaces, fl, qr = build_problem(sample_cols, MESH_N)
+    pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
+
+    def step():
+        for _, form, deg in fl:
+            oracle.assemble_matrix(form, [qr], nthreads=threads, pattern=pats[deg])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = len(fl) * mesh.num_cells / dt
+    sample = f"{sample_cols}x{MESH_N} cell slab ({mesh.num_cells} cells, {qr.num_points} points) of the 2048x2048 workload, all 4 forms per step"
+    line = {
+        "impl": "reference", "metric": "element_tensors_per_s", "value": value, "unit": "element tensors/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "element tensors/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "element tensors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "csr_nnz_per_s": 2 * (pats[1].nnz + pats[2].nnz) / dt,
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"2-D Q1+Q2 stiffness+mass, {MESH_N * n_gpus}x{MESH_N} quad mesh ({MESH_N}x{MESH_N} per GPU), synthetic ragged runtime quadrature U{{{NQ_LO}..{NQ_HI}}} pts/cell, all cells listed (BASELINE.json configs[1])",
+        "cells_per_gpu": MESH_N * MESH_N, "forms": [f[0] for f in FORMS], "mean_points_per_cell": (NQ_LO + NQ_HI) / 2,
+        "l2": "inputs (>= 4 GB of points per pass) are larger than the 126 MB L2; no explicit flush",
+        "parallelism": f"cells{n_gpus}" if n_gpus > 1 else "single",
+    }  # fmt: skip
+
+
+def cpu_baseline_sample():
+    """Oracle (port) on the GPU box's host cores: a bounded sample of the same workload."""
+    from oracle import oracle
+    from customquad_b200.sparsity import build_pattern
+
+    threads = oracle.max_threads()
+    cols = 512  # 512 x 2048 = 1,048,576 cells (a quarter of the workload), all 4 forms once
+    mesh, spaces, fl, qr = build_problem(cols, MESH_N)
+    pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
+    oracle.assemble_matrix(fl[0][1], [qr.select(np.arange(4096))], nthreads=threads, pattern=pats[1])  # warm up threads
+    t0 = time.perf_counter()
+    for _, form, deg in fl:
+        oracle.assemble_matrix(form, [qr], nthreads=threads, pattern=pats[deg])
+    dt = time.perf_counter() - t0
+    return {"value": len(fl) * mesh.num_cells / dt, "unit": "element tensors/s", "cores": threads, "kind": "port", "seconds": dt,
+            "sample": f"{cols}x{MESH_N} cell slab ({mesh.num_cells} cells, {qr.num_points} points) of the workload, all 4 forms once; oracle/cq_oracle.c allocation-free flavour, OpenMP over cells"}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import customquad_b200 as cq  # noqa: F401
+    from customquad_b200 import _lib, assemble as asm
+    from customquad_b200.quadrature import RaggedQuadrature
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+
+    mesh, spaces, fl, qr = build_problem(MESH_N, MESH_N, col0=rank * MESH_N, total_nx=MESH_N * world)
+    C_cells, P_pts = qr.num_entries, qr.num_points
+    mats = {name: asm.create_matrix(form) for name, form, _ in fl}
+    exch = None
+    if world > 1:
+        from customquad_b200 import dist as cqdist
+
+        exch = {name: cqdist.SlabExchange(spaces[deg], mats[name], rank, world) for name, _, deg in fl}
+    asm.qr_on_device(qr, dev)  # inputs resident in HBM before the timed region
+    ctx_launch0 = None
+
+    def step(events=None):
+        for i, (name, form, _) in enumerate(fl):
+            A = mats[name]
+            if events is not None:
+                events[i][0].record()
+            A.data.zero_()  # A.zeroEntries() (assemble_matrix.py:20)
+            asm.assemble_matrix(form, [qr], A=A)
+            if exch is not None:
+                exch[name].exchange()
+            if events is not None:
+                events[i][1].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    for name in mats:
+        mats[name].assemble()  # checks the sparsity error flag once, outside the timed region
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in fl] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = _lib.launch_count(local_rank)
+    wall0 = time.time()
+    t_start.record()
+    for s in range(args.steps):
+        step(ev[s])
+    t_end.record()
+    barrier()
+    wall1 = time.time()
+    launches = _lib.launch_count(local_rank) - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    ms_step = ms_total / args.steps
+    per_form_ms = [float(np.mean([ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)])) for i in range(len(fl))]
+
+    # ---- per-kernel roofline (kernel-only times: separate pass, events around the launch alone) ----
+    peak, peak_src = measured_peak()
+    kern = []
+    for i, (name, form, deg) in enumerate(fl):
+        A = mats[name]
+        ts = []
+        for _ in range(max(3, args.steps)):
+            A.data.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            asm.assemble_matrix(form, [qr], A=A)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts))
+        n = (deg + 1) ** 2
+        ab = algorithmic_bytes(C_cells, P_pts, 2, 4, n, mesh.geometry.x.shape[0], A.nnz)
+        kern.append({"kernel": name, "ms": ms, "algorithmic_bytes": ab, "achieved_gbs": ab / ms / 1e6, "frac": ab / ms / 1e6 / peak,
+                     "nnz": A.nnz, "cells_per_s": C_cells / ms * 1e3})  # fmt: skip
+    dom = max(kern, key=lambda k: k["ms"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom["kernel"])
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "per_kernel": kern}  # fmt: skip
+
+    # ---- end to end: host (pinned) qr buffers in, CSR values out to pinned host memory --------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+        hq = RaggedQuadrature(pin(qr.cells), pin(qr.offsets), pin(qr.pts), pin(qr.w), None, 2)
+        hq_np = RaggedQuadrature(hq.cells.numpy(), hq.offsets.numpy(), hq.pts.numpy(), hq.w.numpy(), None, 2)
+        vals = {name: torch.empty(mats[name].nnz, dtype=torch.float64).pin_memory() for name in mats}
+
+        def e2e_step():
+            for name, form, _ in fl:
+                asm.assemble_matrix_host(form, hq_np, mats[name], vals[name])
+                if exch is not None:
+                    exch[name].exchange()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e_steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = len(fl) * (qr.cells.nbytes + qr.offsets.nbytes + qr.pts.nbytes + qr.w.nbytes)
+        d2h = sum(8 * mats[name].nnz for name in mats)
+        e2e = {"value": len(fl) * C_cells * world / dt, "unit": "element tensors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "api": "cq_assemble_matrix_host (pinned host qr in, CSR values out)"}  # fmt: skip
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_sample()
+    line = {
+        "metric": "element_tensors_per_s", "value": len(fl) * C_cells * world / (ms_step * 1e-3), "unit": "element tensors/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+        "csr_nnz_per_s": sum(mats[n].nnz for n in mats) * world / (ms_step * 1e-3),
+        "per_form_ms": dict(zip([f[0] for f in fl], per_form_ms)),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }  # fmt: skip
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
