@@ -40,6 +40,11 @@ XMIN, XMAX = [-1.11, -1.51], [1.55, 1.22]  # demo/poisson.py:42-43
 FORMS = [("q1_stiffness", 1, "stiffness"), ("q1_mass", 1, "mass"), ("q2_stiffness", 2, "stiffness"), ("q2_mass", 2, "mass")]
 
 
+def log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -193,6 +198,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
 
+    log("building problem")
     mesh, spaces, fl, qr = build_problem(MESH_N, MESH_N, col0=rank * MESH_N, total_nx=MESH_N * world)
     C_cells, P_pts = qr.num_entries, qr.num_points
     mats = {name: asm.create_matrix(form) for name, form, _ in fl}
@@ -251,6 +257,7 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
     per_form_ms = [float(np.mean([ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)])) for i in range(len(fl))]
 
+    log(f"timed region done: {ms_step:.3f} ms/step")
     # ---- per-kernel roofline (kernel-only times: separate pass, events around the launch alone) ----
     peak, peak_src = measured_peak()
     kern = []
@@ -281,6 +288,7 @@ def run_gpu(args):
     # ---- end to end: host (pinned) qr buffers in, CSR values out to pinned host memory --------------
     e2e = None
     if not args.no_e2e:
+        log("e2e: pinning host buffers")
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
         hq = RaggedQuadrature(pin(qr.cells), pin(qr.offsets), pin(qr.pts), pin(qr.w), None, 2)
         hq_np = RaggedQuadrature(hq.cells.numpy(), hq.offsets.numpy(), hq.pts.numpy(), hq.w.numpy(), None, 2)
@@ -292,9 +300,11 @@ def run_gpu(args):
                 if exch is not None:
                     exch[name].exchange()
 
+        log("e2e: warm-up")
         for _ in range(2):
             e2e_step()
         barrier()
+        log("e2e: timing")
         e_steps = max(2, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(e_steps):
@@ -316,7 +326,9 @@ def run_gpu(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu:
+        log("cpu baseline sample")
         cpu = cpu_baseline_sample()
+        log("cpu baseline done")
     line = {
         "metric": "element_tensors_per_s", "value": len(fl) * C_cells * world / (ms_step * 1e-3), "unit": "element tensors/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

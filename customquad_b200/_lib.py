@@ -59,7 +59,7 @@ _SIGNATURES = {
     "cq_assemble_scalar": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_tabulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_element_tensors": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
-    "cq_csr_accumulate_rows": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cq_csr_accumulate_rows": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_axpy": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_matrix_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_vector_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -79,6 +79,16 @@ __global__ void accumulate_kernel(double* __restrict__ y, const double* __restri
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
 }
 
+// values[indptr[row0 + r] + i] += recv[recv_indptr[r] + i]: one warp per row
+__global__ void accumulate_rows_kernel(double* __restrict__ values, const int64_t* __restrict__ indptr, int64_t row0, int64_t nrows,
+                                       const int64_t* __restrict__ recv_indptr, const double* __restrict__ recv) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t dst = indptr[row0 + r], src = recv_indptr[r], n = recv_indptr[r + 1] - src;
+    for (int64_t i = lane; i < n; i += 32) values[dst + i] += recv[src + i];
+  }
+}
+
 // call_basix on the device: one thread per (point, dof)
 template <int DIM, int DEG>
 __global__ void tabulate_kernel(const double* __restrict__ pts, int64_t nq, int deriv, double* __restrict__ out) {
@@ -244,23 +254,17 @@ int cq_tabulate(cq_ctx* ctx, int cell_type, int degree, int basix_derivative, in
   return check_cuda(cudaGetLastError(), "tabulate_kernel launch");
 }
 
-int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t nrows, const double* recv, void* stream) {
-  if (!ctx || !A || !A->indptr || !A->values || (!recv && nrows > 0)) { set_error("null argument"); return CQ_ERR_INVALID; }
+int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t nrows, const int64_t* recv_indptr,
+                           const double* recv, void* stream) {
+  if (!ctx || !A || !A->indptr || !A->values || (nrows > 0 && (!recv || !recv_indptr))) { set_error("null argument"); return CQ_ERR_INVALID; }
   if (row0 < 0 || nrows < 0 || row0 + nrows > A->num_rows) { set_error("row range out of bounds"); return CQ_ERR_INVALID; }
   if (nrows == 0) return CQ_OK;
   if (int rc = set_device(ctx)) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // the row range is contiguous in CSR storage: [indptr[row0], indptr[row0+nrows])
-  int64_t range[2];
-  if (int rc = check_cuda(cudaMemcpyAsync(&range[0], A->indptr + row0, sizeof(int64_t), cudaMemcpyDeviceToHost, s), "indptr D2H")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(&range[1], A->indptr + row0 + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s), "indptr D2H")) return rc;
-  if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
-  const int64_t n = range[1] - range[0];
-  if (n <= 0) return CQ_OK;
-  const int grid = (int)((n + 255) / 256 < (int64_t)ctx->num_sms * 8 ? (n + 255) / 256 : (int64_t)ctx->num_sms * 8);
-  accumulate_kernel<<<grid, 256, 0, s>>>(A->values + range[0], recv, n);
+  const int64_t warps = nrows;  // one warp per row
+  const int grid = (int)((warps + 7) / 8 < (int64_t)ctx->num_sms * 8 ? (warps + 7) / 8 : (int64_t)ctx->num_sms * 8);
+  accumulate_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A->values, A->indptr, row0, nrows, recv_indptr, recv);
   ctx->launches++;
-  return check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+  return check_cuda(cudaGetLastError(), "accumulate_rows_kernel launch");
 }
 
 int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream) {

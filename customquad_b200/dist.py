@@ -1,0 +1,205 @@
+"""Cell-partitioned assembly across the GPUs of one box.
+
+The reference is serial; the only analogue of this step is PETSc's
+MatAssemblyBegin/End stash that ``A.assemble()`` triggers (reference README.md:95,
+demo/poisson.py:194).  Here: one process per GPU; the mesh is cut into R slabs along the slowest
+cell axis (x for quads, z for hexes); rank r assembles the cells of slab r.  Every rank numbers
+dofs on its slab *plus one ghost layer of cells below it* (so that its rows can hold the
+couplings to the neighbour's dofs), owns the dof lattice lines above that ghost layer, and ships
+the contributions it made to the one lattice line it does not own -- the top line of its slab,
+owned by rank r+1 -- to that neighbour (NCCL send/recv through torch.distributed), which adds
+them into its rows.  Rows are lattice-line-major, so both the ghost rows on the sender and the
+interface rows on the receiver are contiguous, and a sender row is a prefix of the receiver's row
+(columns are ordered line-major, the sender only knows the lines at or below the interface):
+no packing kernel, no index exchange.
+
+Scalars are all-reduced; vectors exchange the same interface line.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .fem import FunctionSpace, FunctionSpaceQ, VectorFunctionSpace  # noqa: F401
+from .mesh import Mesh, create_box, create_rectangle
+
+
+@dataclass
+class Slab:
+    """What rank `rank` of `world` works on."""
+
+    mesh: Mesh            # slab + ghost layer (ghost cells first along the slab axis)
+    cells: np.ndarray     # local ids of the cells this rank assembles (ghost layer excluded)
+    first: int            # first global cell layer of the slab
+    count: int            # cell layers in the slab
+    ghost: int            # 1 if a ghost layer of cells was prepended, else 0
+    rank: int
+    world: int
+
+
+def partition_layers(n_layers: int, world: int, weights=None) -> np.ndarray:
+    """Slab boundaries [world+1] along the slab axis.  With `weights` (work per layer, e.g. the sum
+    of nq*n^2 over the layer's cells) the split balances work, not cell count."""
+    if weights is None:
+        return np.array([n_layers * r // world for r in range(world + 1)], dtype=np.int64)
+    w = np.asarray(weights, dtype=np.float64)
+    assert w.shape[0] == n_layers
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    b = np.searchsorted(cum, cum[-1] * np.arange(1, world) / world, side="left")
+    b = np.concatenate([[0], b, [n_layers]]).astype(np.int64)
+    for r in range(1, world + 1):  # every rank keeps at least one layer
+        b[r] = max(b[r], b[r - 1] + 1)
+    b[world] = n_layers
+    for r in range(world - 1, 0, -1):
+        b[r] = min(b[r], b[r + 1] - 1)
+    return b
+
+
+def make_slab(points, n, rank: int, world: int, bounds=None) -> Slab:
+    """Slab `rank` of the global tensor mesh ``create_rectangle/create_box(points, n)``."""
+    p = np.asarray(points, dtype=np.float64)
+    n = [int(v) for v in n]
+    tdim = len(n)
+    axis = 0 if tdim == 2 else 2  # slowest cell axis of the mesh generators
+    b = partition_layers(n[axis], world) if bounds is None else np.asarray(bounds)
+    first, last = int(b[rank]), int(b[rank + 1])
+    ghost = 1 if rank > 0 else 0
+    lo = first - ghost
+    h = (p[1, axis] - p[0, axis]) / n[axis]
+    q = p.copy()
+    q[0, axis] = p[0, axis] + lo * h
+    q[1, axis] = p[0, axis] + last * h
+    nn = list(n)
+    nn[axis] = last - lo
+    mesh = (create_rectangle if tdim == 2 else create_box)(q, nn)
+    per_layer = mesh.num_cells // nn[axis]
+    cells = np.arange(ghost * per_layer, mesh.num_cells, dtype=np.int32)  # layers are the slowest cell index
+    return Slab(mesh, cells, first, last - first, ghost, rank, world)
+
+
+class SlabExchange:
+    """Interface-row exchange for one matrix (or vector) of a slab-partitioned assembly.
+
+    ``accumulate_rows(values, indptr, row0, nrows, recv_indptr, recv)`` and ``axpy(n, x, y)`` are
+    the receive-side adds; by default they are the CUDA kernels behind cq_csr_accumulate_rows /
+    cq_axpy (there is no CPU fallback; the gloo tests inject numpy doubles for the host logic).
+    """
+
+    def __init__(self, V: FunctionSpace, slab: Slab, indptr=None, accumulate_rows=None, axpy=None, group=None):
+        self.V, self.slab, self.group = V, slab, group
+        k, bs = V.degree, V.bs
+        lshape = V.lattice_shape
+        tdim = len(lshape)
+        # dofs per lattice line/plane orthogonal to the slab axis (line-major numbering, fem.py)
+        self.line = (lshape[1] if tdim == 2 else lshape[0] * lshape[1]) * bs
+        nlines = lshape[0] if tdim == 2 else lshape[2]
+        self.nrows = nlines * self.line
+        self.has_up = slab.rank < slab.world - 1      # sends its top line to rank+1
+        self.has_down = slab.rank > 0                 # receives rank-1's top line
+        self.send_row0 = (nlines - 1) * self.line     # ghost rows (not owned): the slab's top line
+        self.recv_row0 = k * slab.ghost * self.line   # the same line in this rank's numbering
+        # rows this rank owns: everything above the ghost layer except the top line (owned by rank+1)
+        self.owned_row0 = self.recv_row0 if self.has_down else 0
+        self.owned_row1 = self.send_row0 if self.has_up else self.nrows
+        self._acc_rows, self._axpy = accumulate_rows, axpy
+        self.recv_indptr = None
+        if indptr is not None:
+            self.set_pattern(indptr)
+
+    # -- matrices ---------------------------------------------------------------------------
+    def set_pattern(self, indptr, indices=None):
+        """Derive, from this rank's own pattern, the lengths of the rows rank-1 will send: the
+        columns of an interface row that lie on lattice lines at or below the interface."""
+        self.indptr = indptr
+        if self.has_down:
+            assert indices is not None, "receiver needs its column indices"
+            r0, r1 = self.recv_row0, self.recv_row0 + self.line
+            ip = _to_numpy(indptr[r0 : r1 + 1])
+            cols = _to_numpy(indices[int(ip[0]) : int(ip[-1])])
+            below = cols < r1  # columns on lines <= interface line  (col id = line*line_size + ...)
+            cnt = np.add.reduceat(below.astype(np.int64), (ip[:-1] - ip[0])) if len(cols) else np.zeros(self.line, np.int64)
+            # prefix property: the `cnt[r]` columns below the interface are the first entries of the row
+            starts = ip[:-1] - ip[0]
+            for r in (0, self.line // 2, self.line - 1):
+                assert below[starts[r] : starts[r] + cnt[r]].all()
+            self.recv_indptr_host = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        if self.has_up:
+            ip = _to_numpy(indptr[self.send_row0 : self.nrows + 1])
+            self.send_lo, self.send_hi = int(ip[0]), int(ip[-1])
+
+    def exchange_matrix(self, values):
+        """values: this rank's CSR data (torch tensor).  After the call the owned rows are complete."""
+        import torch
+        import torch.distributed as dist
+
+        ops, recv = [], None
+        if self.has_up:
+            ops.append(dist.P2POp(dist.isend, values[self.send_lo : self.send_hi], self.slab.rank + 1, self.group))
+        if self.has_down:
+            recv = torch.empty(int(self.recv_indptr_host[-1]), dtype=values.dtype, device=values.device)
+            ops.append(dist.P2POp(dist.irecv, recv, self.slab.rank - 1, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if recv is not None:
+            if self.recv_indptr is None or self.recv_indptr.device != values.device:
+                self.recv_indptr = torch.from_numpy(self.recv_indptr_host).to(values.device)
+            (self._acc_rows or _cuda_accumulate_rows)(values, self.indptr, self.recv_row0, self.line, self.recv_indptr, recv)
+
+    # -- vectors ----------------------------------------------------------------------------
+    def exchange_vector(self, b):
+        import torch
+        import torch.distributed as dist
+
+        ops, recv = [], None
+        if self.has_up:
+            ops.append(dist.P2POp(dist.isend, b[self.send_row0 : self.nrows], self.slab.rank + 1, self.group))
+        if self.has_down:
+            recv = torch.empty(self.line, dtype=b.dtype, device=b.device)
+            ops.append(dist.P2POp(dist.irecv, recv, self.slab.rank - 1, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if recv is not None:
+            (self._axpy or _cuda_axpy)(self.line, recv, b[self.recv_row0 : self.recv_row0 + self.line])
+
+    # -- scalars ----------------------------------------------------------------------------
+    @staticmethod
+    def reduce_scalar(m, device=None, group=None) -> float:
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([m], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return float(t.item())
+
+
+def _to_numpy(t):
+    return t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+
+
+def _cuda_accumulate_rows(values, indptr, row0, nrows, recv_indptr, recv):
+    import ctypes as C
+
+    from . import _lib
+
+    assert values.is_cuda, "no CPU fallback: the receive-side add is a CUDA kernel"
+    import torch
+
+    L = _lib.load()
+    A = _lib.CsrDesc(int(indptr.shape[0] - 1), int(values.shape[0]), C.c_void_p(indptr.data_ptr()), None, C.c_void_p(values.data_ptr()))
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.cq_csr_accumulate_rows(_lib.ctx(values.device.index), C.byref(A), row0, nrows, C.c_void_p(recv_indptr.data_ptr()), C.c_void_p(recv.data_ptr()), s))
+
+
+def _cuda_axpy(n, x, y):
+    import ctypes as C
+
+    from . import _lib
+
+    assert y.is_cuda, "no CPU fallback: the receive-side add is a CUDA kernel"
+    import torch
+
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.load().cq_axpy(_lib.ctx(y.device.index), int(n), C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), s))

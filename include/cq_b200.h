@@ -182,10 +182,12 @@ int cq_element_tensors(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
                        const cq_space* space, const cq_quadrature* qr, double* out, void* stream);
 
 /* ---- multi-GPU receive side --------------------------------------------------------------- */
-/* values[indptr[row0] + i] += recv[i] for the nnz of rows [row0, row0 + nrows): adds a
- * neighbour rank's contributions to rows this rank owns. */
+/* For r in [0, nrows): values[indptr[row0 + r] + i] += recv[recv_indptr[r] + i],
+ * i < recv_indptr[r+1] - recv_indptr[r].  Adds a neighbour rank's contributions to rows this
+ * rank owns; a sender row is a prefix of the owner's row (customquad_b200/dist.py).
+ * recv_indptr [nrows + 1] int64 and recv are device pointers. */
 int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t nrows,
-                           const double* recv, void* stream);
+                           const int64_t* recv_indptr, const double* recv, void* stream);
 /* y[i] += x[i], i < n (vector interface dofs) */
 int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream);
 

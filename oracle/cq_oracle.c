@@ -489,3 +489,16 @@ int cq_oracle_max_threads(void) {
   return 1;
 #endif
 }
+
+/* Debug aid: print a native backtrace on SIGSEGV (set CQ_ORACLE_BACKTRACE=1 in oracle.py). */
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void segv_handler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+void cq_oracle_install_segv_handler(void) { signal(SIGSEGV, segv_handler); }

@@ -27,7 +27,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "cq_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "cq_b200.h")
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        base = ["gcc", "-O2", "-fPIC", "-Wall", "-std=c11", "-D_GNU_SOURCE", "-shared", "-o", so, src, "-lm"]
+        base = ["gcc", "-O2", "-g", "-fPIC", "-Wall", "-std=c11", "-D_GNU_SOURCE", "-shared", "-o", so, src, "-lm"]
         r = subprocess.run(base[:1] + ["-fopenmp"] + base[1:], capture_output=True, text=True)
         if r.returncode != 0:  # toolchain without libgomp: serial oracle
             subprocess.run(base, check=True)
@@ -49,10 +49,23 @@ def lib():
     global _LIB
     if _LIB is None:
         L = C.CDLL(build())
-        for name in ("cq_oracle_assemble_matrix", "cq_oracle_assemble_vector", "cq_oracle_assemble_scalar", "cq_oracle_element_tensors"):
-            getattr(L, name).restype = C.c_int64
+        # argtypes are mandatory: without them ctypes passes Python ints as 32-bit C ints and
+        # truncates the addresses of large (mmap'd) numpy arrays.
+        P = C.c_void_p
+        L.cq_oracle_assemble_matrix.restype = C.c_int64
+        L.cq_oracle_assemble_matrix.argtypes = [C.POINTER(_Args), P, P, P]
+        L.cq_oracle_assemble_vector.restype = C.c_int64
+        L.cq_oracle_assemble_vector.argtypes = [C.POINTER(_Args), P]
+        L.cq_oracle_assemble_scalar.restype = C.c_int64
+        L.cq_oracle_assemble_scalar.argtypes = [C.POINTER(_Args), P]
+        L.cq_oracle_element_tensors.restype = C.c_int64
+        L.cq_oracle_element_tensors.argtypes = [C.POINTER(_Args), C.c_int, P]
+        L.cq_oracle_max_threads.restype = C.c_int
+        L.cq_oracle_max_threads.argtypes = []
         L.cq_oracle_tabulate.restype = C.c_int
         L.cq_oracle_tabulate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        if os.environ.get("CQ_ORACLE_BACKTRACE"):
+            L.cq_oracle_install_segv_handler()
         _LIB = L
     return _LIB
 
