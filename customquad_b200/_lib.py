@@ -23,7 +23,7 @@ class MeshDesc(C.Structure):
 
 
 class SpaceDesc(C.Structure):
-    _fields_ = [("num_dofs", C.c_int64), ("dofmap", C.c_void_p), ("coeffs", C.c_void_p)]
+    _fields_ = [("num_dofs", C.c_int64), ("dofmap", C.c_void_p), ("coeffs", C.c_void_p), ("elem_pos", C.c_void_p)]
 
 
 class QuadratureDesc(C.Structure):
@@ -57,6 +57,8 @@ _SIGNATURES = {
     "cq_assemble_matrix": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p]),
     "cq_assemble_vector": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+    "cq_scatter_map_stride": (C.c_int, [C.c_int, C.c_int]),
+    "cq_build_scatter_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_tabulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_element_tensors": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_csr_accumulate_rows": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -72,6 +72,28 @@ def pattern_on_device(V, dev, cells=None):
     return V._dev[key]
 
 
+def scatter_map_on_device(V, dev, indptr, indices):
+    """cq_build_scatter_map: per-cell positions of the element tensor entries inside their CSR
+    rows, built once per (space, pattern) -- the stand-in for the local-to-global mapping and
+    preallocation a PETSc Mat carries.  Returns None when a row is too long for the uint8 map
+    (the kernels then search the rows like MatSetValuesLocal does)."""
+    torch = _torch()
+    key = ("scatter_map", dev, indptr.data_ptr())
+    if key not in V._dev:
+        L = _lib.load()
+        stride = L.cq_scatter_map_stride(int(V.mesh.cell_type), int(V.degree))
+        dm = space_on_device(V, dev)
+        out = torch.empty((dm.shape[0], stride), dtype=torch.uint8, device=dev)
+        A = _lib.CsrDesc(V.num_dofs, int(indices.shape[0]), _ptr(indptr), _ptr(indices), None)
+        rc = L.cq_build_scatter_map(_lib.ctx(dev.index), int(V.mesh.cell_type), int(V.degree), int(V.bs), dm.shape[0], _ptr(dm), C.byref(A), _ptr(out), _stream_ptr())
+        if rc == -3:  # CQ_ERR_UNSUPPORTED: rows longer than 255
+            out = None
+        else:
+            _lib.check(rc)
+        V._dev[key] = out
+    return V._dev[key]
+
+
 def coefficient_on_device(f, dev):
     """dolfinx.cpp.fem.pack_coefficients (assemble_matrix.py:16): [num_cells, n*bs]."""
     torch = _torch()
@@ -96,7 +118,7 @@ def qr_on_device(q: RaggedQuadrature, dev):
 class _Call:
     """Everything one C-ABI call needs, kept alive for the duration of the call."""
 
-    def __init__(self, form: Form, qr, dev, host_qr: bool = False):
+    def __init__(self, form: Form, qr, dev, host_qr: bool = False, A: CSRMatrix | None = None):
         mesh = form.mesh
         gdim = mesh.geometry.dim
         self.q = normalise_qr(qr, gdim)
@@ -113,8 +135,10 @@ class _Call:
         if self.V is not None:
             dm = space_on_device(self.V, dev)
             co = coefficient_on_device(form.coefficient, dev) if form.coefficient is not None else None
-            self.keep += [dm, co]
-            self.space = _lib.SpaceDesc(self.V.dofmap.num_dofs, _ptr(dm), _ptr(co))
+            # the map belongs to the full-form pattern; matrices on a "cells" pattern search their rows
+            pos = scatter_map_on_device(self.V, dev, A.indptr, A.indices) if (A is not None and A.full_pattern) else None
+            self.keep += [dm, co, pos]
+            self.space = _lib.SpaceDesc(self.V.dofmap.num_dofs, _ptr(dm), _ptr(co), _ptr(pos))
         consts = form.consts()
         self._consts = (C.c_double * max(1, consts.size))(*consts.tolist())
         self.form = _lib.FormDesc(int(form.kind), int(mesh.cell_type), int(form.degree), int(form.bs), int(form.fn_kind), int(consts.size), self._consts)
@@ -140,7 +164,9 @@ def create_matrix(form: Form, pattern_cells=None) -> CSRMatrix:
     indptr, indices = pattern_on_device(V, dev, pattern_cells)
     data = torch.zeros(indices.shape[0], dtype=torch.float64, device=dev)
     n = V.num_dofs
-    return CSRMatrix(indptr, indices, data, (n, n), dev.index, _stream_ptr())
+    A = CSRMatrix(indptr, indices, data, (n, n), dev.index, _stream_ptr())
+    A.full_pattern = pattern_cells is None
+    return A
 
 
 def _csr_desc(A: CSRMatrix):
@@ -162,7 +188,7 @@ def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: st
         A = create_matrix(form, cells)
     csr = _csr_desc(A)
     for i, _id in enumerate(ids):  # qr tuples are matched to integrals by position (:26,42)
-        c = _Call(form, qr_data[i], dev)
+        c = _Call(form, qr_data[i], dev, A=A)
         _lib.check(L.cq_assemble_matrix(ctx, C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), _stream_ptr()))
     A.assembled = False
     return A
@@ -232,7 +258,7 @@ def assemble_matrix_host(form: Form, q: RaggedQuadrature, A: CSRMatrix, values_h
     is a float64 host buffer of A.nnz entries."""
     L = _lib.load()
     dev = _dev()
-    c = _Call(form, q, dev, host_qr=True)
+    c = _Call(form, q, dev, host_qr=True, A=A)
     csr = _csr_desc(A)
     vh = C.c_void_p(values_host.ctypes.data if isinstance(values_host, np.ndarray) else values_host.data_ptr())
     _lib.check(L.cq_assemble_matrix_host(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), vh, _stream_ptr()))
@@ -253,3 +279,10 @@ def assemble_scalar_host(form: Form, q: RaggedQuadrature) -> float:
     m = np.zeros(1)
     _lib.check(L.cq_assemble_scalar_host(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.c_void_p(m.ctypes.data), _stream_ptr()))
     return float(m[0])
+
+
+def set_variant(variant: int) -> None:
+    """Kernel choice for the current device: 0 auto (staged bulk-copy kernel when applicable),
+    1 direct-load kernel only, 2 staged kernel only (raises when not applicable)."""
+    dev = _dev()
+    _lib.check(_lib.load().cq_ctx_set_variant(_lib.ctx(dev.index), int(variant)))

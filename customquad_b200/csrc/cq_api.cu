@@ -66,6 +66,9 @@ static int pack(cq_ctx* ctx, const cq_form_desc* f, const cq_mesh* mesh, const c
   P.dofmap = space ? space->dofmap : nullptr;
   P.coeffs = space ? space->coeffs : nullptr;
   P.err_flag = ctx->err_flag;
+  P.elem_pos = space ? space->elem_pos : nullptr;
+  P.work_counter = ctx->work_counter;
+  P.num_points = qr->num_points;
   P.bs = f->bs;
   for (int i = 0; i < f->nconsts; ++i) P.p[i] = f->consts[i];
   P.betaN = nitsche ? (f->nconsts > 0 ? f->consts[0] : 0.0) : 0.0;
@@ -86,6 +89,23 @@ __global__ void accumulate_rows_kernel(double* __restrict__ values, const int64_
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int64_t dst = indptr[row0 + r], src = recv_indptr[r], n = recv_indptr[r + 1] - src;
     for (int64_t i = lane; i < n; i += 32) values[dst + i] += recv[src + i];
+  }
+}
+
+// scatter positions: one thread per (cell, i, j)
+__global__ void scatter_map_kernel(const int32_t* __restrict__ dofmap, int64_t num_cells, int n, int stride, int bs,
+                                   const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                   uint8_t* __restrict__ out, int* err) {
+  const int64_t total = num_cells * n * n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / (n * n);
+    const int ij = (int)(t - c * n * n), i = ij / n, j = ij - i * n;
+    const int64_t row = (int64_t)dofmap[c * n + i] * bs;
+    const int32_t col = dofmap[c * n + j] * bs;
+    const int64_t s = csr_find(indptr, indices, row, col);
+    const int64_t rel = s < 0 ? -1 : (s - indptr[row]) / bs;
+    if (s < 0 || rel > 255 || (s - indptr[row]) % bs != 0) atomicExch(err, s < 0 ? 1 : 2);
+    out[c * stride + ij] = (uint8_t)(rel < 0 ? 0 : rel);
   }
 }
 
@@ -135,6 +155,8 @@ int cq_ctx_create(int device, cq_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   int rc = check_cuda(cudaMalloc(&c->err_flag, sizeof(int)), "cudaMalloc(err_flag)");
   if (!rc) rc = check_cuda(cudaMemset(c->err_flag, 0, sizeof(int)), "cudaMemset(err_flag)");
+  if (!rc) rc = check_cuda(cudaMalloc(&c->work_counter, sizeof(unsigned int)), "cudaMalloc(work_counter)");
+  if (!rc) rc = check_cuda(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), "cudaDeviceGetAttribute");
   if (!rc) rc = check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   for (int i = 0; i < 8 && !rc; ++i) rc = check_cuda(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming), "cudaEventCreate");
   if (!rc) rc = check_cuda(cudaHostAlloc(&c->host_flag, sizeof(int), cudaHostAllocDefault), "cudaHostAlloc");
@@ -147,6 +169,7 @@ int cq_ctx_destroy(cq_ctx* ctx) {
   if (!ctx) return CQ_OK;
   cudaSetDevice(ctx->device);
   if (ctx->err_flag) cudaFree(ctx->err_flag);
+  if (ctx->work_counter) cudaFree(ctx->work_counter);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->scalar_dev) cudaFree(ctx->scalar_dev);
   if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
@@ -230,6 +253,37 @@ int cq_element_tensors(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
     case 1: return launch_vector(ctx, *form, P, s);
     default: return launch_scalar(ctx, *form, P, s);
   }
+}
+
+int cq_scatter_map_stride(int cell_type, int degree) {
+  if ((cell_type != CQ_CELL_QUADRILATERAL && cell_type != CQ_CELL_HEXAHEDRON) || (degree != 1 && degree != 2)) return -1;
+  int n = degree + 1;
+  n = cell_type == CQ_CELL_QUADRILATERAL ? n * n : n * n * n;
+  return (n * n + 15) / 16 * 16;
+}
+
+int cq_build_scatter_map(cq_ctx* ctx, int cell_type, int degree, int bs, int64_t num_cells, const int32_t* dofmap,
+                         const cq_csr* A, uint8_t* out, void* stream) {
+  const int stride = cq_scatter_map_stride(cell_type, degree);
+  if (!ctx || !dofmap || !A || !A->indptr || !A->indices || !out || stride < 0 || bs < 1 || bs > 3) { set_error("bad argument"); return CQ_ERR_INVALID; }
+  if (num_cells <= 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  int n = degree + 1;
+  n = cell_type == CQ_CELL_QUADRILATERAL ? n * n : n * n * n;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = check_cuda(cudaMemsetAsync(out, 0, (size_t)num_cells * stride, s), "memset map")) return rc;
+  const int64_t total = num_cells * n * n;
+  const int grid = (int)((total + 255) / 256 < (int64_t)ctx->num_sms * 16 ? (total + 255) / 256 : (int64_t)ctx->num_sms * 16);
+  scatter_map_kernel<<<grid, 256, 0, s>>>(dofmap, num_cells, n, stride, bs, A->indptr, A->indices, out, ctx->err_flag);
+  ctx->launches++;
+  if (int rc = check_cuda(cudaGetLastError(), "scatter_map_kernel launch")) return rc;
+  // setup call: synchronous check so the caller knows whether the map is usable
+  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "err_flag D2H")) return rc;
+  if (int rc = check_cuda(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s), "err_flag reset")) return rc;
+  if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
+  if (*ctx->host_flag == 1) { set_error("scatter map: a (row, col) of the dofmap is absent from the CSR pattern"); return CQ_ERR_SPARSITY; }
+  if (*ctx->host_flag == 2) { set_error("scatter map: a row holds more than 255 scalar entries"); return CQ_ERR_UNSUPPORTED; }
+  return CQ_OK;
 }
 
 int cq_tabulate(cq_ctx* ctx, int cell_type, int degree, int basix_derivative, int64_t num_points, const double* pts,

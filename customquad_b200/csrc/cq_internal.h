@@ -13,6 +13,8 @@ struct cq_ctx {
   int num_sms = 0;
   int variant = 0;
   int* err_flag = nullptr;  // device
+  unsigned int* work_counter = nullptr;  // device: dynamic stage counter of the staged kernels
+  int max_smem_optin = 0;
   std::atomic<int64_t> launches{0};
   // end-to-end (host buffer) path: grow-only device staging + a copy stream
   cudaStream_t copy_stream = nullptr;

@@ -30,6 +30,10 @@ struct KParams {
   double* values;  // CSR values (matrix)
   double* out;     // vector b / scalar m / element tensors
   int* err_flag;
+  const uint8_t* __restrict__ elem_pos;  // scatter positions [num_cells, NPOS] or null
+  unsigned int* work_counter;            // ctx-owned, zeroed before a staged launch
+  int64_t num_points;                    // length of pts / w (bulk-copy tail handling)
+  int stage_points;                      // points capacity of one smem stage
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)
   int elem_out;    // 1: write un-scattered element tensors to out[k, :]
   double betaN;

@@ -1,0 +1,76 @@
+// cq_launch.cuh -- launch helpers shared by the cq_launch_*.cu translation units: the direct
+// (grid-strided) kernel and the bulk-copy staged persistent kernel, and the choice between them.
+#pragma once
+#include "cq_internal.h"
+#include "cq_staged.cuh"
+
+namespace cq {
+
+template <class T, int G>
+static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
+  constexpr int THREADS = 256;
+  constexpr int64_t ENTRIES_PER_BLOCK = (THREADS / 32) * (32 / G);
+  const int grid = grid_for<assemble_direct_kernel<T, G, THREADS>>(ctx, THREADS, ENTRIES_PER_BLOCK, P.num_entries);
+  assemble_direct_kernel<T, G, THREADS><<<grid, THREADS, 0, s>>>(P);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "assemble_direct_kernel launch");
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Can this call run the staged kernel?  (Otherwise the direct kernel handles it.)
+template <class T>
+static bool staged_ok(const cq_ctx* ctx, const KParams& P) {
+  if (ctx->variant == 1 || P.elem_out) return false;
+  if (T::RANK == 2 && !P.elem_pos) return false;  // needs the scatter map (cq_build_scatter_map)
+  if (!aligned16(P.pts) || !aligned16(P.w) || (T::NEED_NORMAL && !aligned16(P.normals))) return false;
+  return true;
+}
+
+template <class T, int G, int NPW, int NCW>
+static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
+  constexpr int CB = 32;
+  using Lay = StagedLayout<T, CB>;
+  auto kernel = assemble_staged_kernel<T, G, NPW, NCW>;
+  // stage capacity: ~1.25x the mean points of 32 entries, bounded by the shared memory per SM
+  const size_t budget = (size_t)ctx->max_smem_optin - 1024;
+  const size_t per_point = (size_t)T::DIM * 8 * (T::NEED_NORMAL ? 2 : 1) + 8;
+  const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
+  if (budget / NPW <= fixed + 64 * per_point) { set_error("staged kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
+  const int64_t pb_max = (int64_t)((budget / NPW - fixed) / per_point) & ~(int64_t)1;
+  int64_t pb = (P.num_points / (P.num_entries > 0 ? P.num_entries : 1) + 1) * CB * 5 / 4 + 64;
+  pb = (pb + 1) & ~(int64_t)1;
+  if (pb > pb_max) pb = pb_max;
+  if (pb < 64) pb = 64;
+  P.stage_points = (int)pb;
+  const size_t smem = NPW * Lay::stage_bytes((int)pb);
+  static thread_local size_t configured = 0;  // per kernel instantiation
+  if (smem > configured) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
+    configured = smem;
+  }
+  if (int rc = check_cuda(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s), "work_counter reset")) return rc;
+  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
+  const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
+  kernel<<<grid, (NPW + NCW) * 32, smem, s>>>(P);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
+}
+
+// consumer warps by accumulator size: the register file holds (NPW + NCW) * 32 threads
+template <class T>
+struct StagedShape {
+  static constexpr int NPW = 4;
+  static constexpr int NCW = T::NACC <= 16 ? 12 : (T::NACC <= 36 ? 6 : 4);
+  static constexpr int G = T::NACC <= 16 ? 4 : 8;
+};
+
+template <class T, int GDIRECT = 8>
+static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
+  using S = StagedShape<T>;
+  if (staged_ok<T>(ctx, P)) return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
+  if (ctx->variant == 2) { set_error("staged kernel requested but not applicable (scatter map / alignment / element output)"); return CQ_ERR_UNSUPPORTED; }
+  return launch_direct<T, GDIRECT>(ctx, P, s);
+}
+
+}  // namespace cq

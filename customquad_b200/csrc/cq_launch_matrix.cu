@@ -1,18 +1,8 @@
 // cq_launch_matrix.cu -- instantiation + dispatch of the rank-2 (bilinear form) kernels
 #include "cq_dmma.cuh"
-#include "cq_internal.h"
+#include "cq_launch.cuh"
 
 namespace cq {
-
-template <class T, int G>
-static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
-  constexpr int THREADS = 256;
-  constexpr int64_t ENTRIES_PER_BLOCK = (THREADS / 32) * (32 / G);
-  const int grid = grid_for<assemble_direct_kernel<T, G, THREADS>>(ctx, THREADS, ENTRIES_PER_BLOCK, P.num_entries);
-  assemble_direct_kernel<T, G, THREADS><<<grid, THREADS, 0, s>>>(P);
-  ctx->launches++;
-  return check_cuda(cudaGetLastError(), "assemble_direct_kernel launch");
-}
 
 template <int FORM>
 static int launch_dmma(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
@@ -26,9 +16,9 @@ static int launch_dmma(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
 template <int FORM>
 static int launch_matrix_form(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s) {
   const bool quad = f.cell_type == CQ_CELL_QUADRILATERAL;
-  if (quad && f.degree == 1) return launch_direct<FormTraits<FORM, 2, 1, 1, CQ_FN_CONST>, 8>(ctx, P, s);
-  if (quad && f.degree == 2) return launch_direct<FormTraits<FORM, 2, 2, 1, CQ_FN_CONST>, 8>(ctx, P, s);
-  if (!quad && f.degree == 1) return launch_direct<FormTraits<FORM, 3, 1, 1, CQ_FN_CONST>, 8>(ctx, P, s);
+  if (quad && f.degree == 1) return launch_auto<FormTraits<FORM, 2, 1, 1, CQ_FN_CONST>>(ctx, P, s);
+  if (quad && f.degree == 2) return launch_auto<FormTraits<FORM, 2, 2, 1, CQ_FN_CONST>>(ctx, P, s);
+  if (!quad && f.degree == 1) return launch_auto<FormTraits<FORM, 3, 1, 1, CQ_FN_CONST>>(ctx, P, s);
   return launch_dmma<FORM>(ctx, P, s);
 }
 

@@ -1,25 +1,15 @@
 // cq_launch_scalar.cu -- instantiation + dispatch of the rank-0 (functional) kernels
-#include "cq_internal.h"
+#include "cq_launch.cuh"
 
 namespace cq {
-
-template <class T, int G>
-static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
-  constexpr int THREADS = 256;
-  constexpr int64_t ENTRIES_PER_BLOCK = (THREADS / 32) * (32 / G);
-  const int grid = grid_for<assemble_direct_kernel<T, G, THREADS>>(ctx, THREADS, ENTRIES_PER_BLOCK, P.num_entries);
-  assemble_direct_kernel<T, G, THREADS><<<grid, THREADS, 0, s>>>(P);
-  ctx->launches++;
-  return check_cuda(cudaGetLastError(), "assemble_direct_kernel launch");
-}
 
 // closed-form data function (u_ex / f): COEF is not a legal choice here
 template <int FORM, int DIM, int DEG, int BS>
 static int launch_analytic(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s) {
   switch (f.fn_kind) {
-    case CQ_FN_CONST: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_CONST>, 8>(ctx, P, s);
-    case CQ_FN_AFFINE: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_AFFINE>, 8>(ctx, P, s);
-    case CQ_FN_SINPROD: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_SINPROD>, 8>(ctx, P, s);
+    case CQ_FN_CONST: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_CONST>>(ctx, P, s);
+    case CQ_FN_AFFINE: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_AFFINE>>(ctx, P, s);
+    case CQ_FN_SINPROD: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_SINPROD>>(ctx, P, s);
     default: set_error("form %d needs a closed-form fn_kind (got %d)", FORM, f.fn_kind); return CQ_ERR_INVALID;
   }
 }
@@ -38,10 +28,10 @@ static int launch_sq(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaS
   if (f.fn_kind != CQ_FN_COEF)  // closed-form f: the element is irrelevant
     return f.bs == 1 ? launch_analytic<FORM, DIM, 1, 1>(ctx, f, P, s) : launch_analytic<FORM, DIM, 1, DIM>(ctx, f, P, s);
   if (f.degree == 1)
-    return f.bs == 1 ? launch_direct<FormTraits<FORM, DIM, 1, 1, CQ_FN_COEF>, 8>(ctx, P, s)
-                     : launch_direct<FormTraits<FORM, DIM, 1, DIM, CQ_FN_COEF>, 8>(ctx, P, s);
-  return f.bs == 1 ? launch_direct<FormTraits<FORM, DIM, 2, 1, CQ_FN_COEF>, 8>(ctx, P, s)
-                   : launch_direct<FormTraits<FORM, DIM, 2, DIM, CQ_FN_COEF>, 8>(ctx, P, s);
+    return f.bs == 1 ? launch_auto<FormTraits<FORM, DIM, 1, 1, CQ_FN_COEF>>(ctx, P, s)
+                     : launch_auto<FormTraits<FORM, DIM, 1, DIM, CQ_FN_COEF>>(ctx, P, s);
+  return f.bs == 1 ? launch_auto<FormTraits<FORM, DIM, 2, 1, CQ_FN_COEF>>(ctx, P, s)
+                   : launch_auto<FormTraits<FORM, DIM, 2, DIM, CQ_FN_COEF>>(ctx, P, s);
 }
 
 int launch_scalar(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s) {

@@ -1,25 +1,15 @@
 // cq_launch_vector.cu -- instantiation + dispatch of the rank-1 (linear form) kernels
-#include "cq_internal.h"
+#include "cq_launch.cuh"
 
 namespace cq {
-
-template <class T, int G>
-static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
-  constexpr int THREADS = 256;
-  constexpr int64_t ENTRIES_PER_BLOCK = (THREADS / 32) * (32 / G);
-  const int grid = grid_for<assemble_direct_kernel<T, G, THREADS>>(ctx, THREADS, ENTRIES_PER_BLOCK, P.num_entries);
-  assemble_direct_kernel<T, G, THREADS><<<grid, THREADS, 0, s>>>(P);
-  ctx->launches++;
-  return check_cuda(cudaGetLastError(), "assemble_direct_kernel launch");
-}
 
 template <int FORM, int DIM, int DEG, int BS>
 static int launch_fn(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s) {
   switch (f.fn_kind) {
-    case CQ_FN_COEF: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_COEF>, 8>(ctx, P, s);
-    case CQ_FN_CONST: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_CONST>, 8>(ctx, P, s);
-    case CQ_FN_AFFINE: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_AFFINE>, 8>(ctx, P, s);
-    case CQ_FN_SINPROD: return launch_direct<FormTraits<FORM, DIM, DEG, BS, CQ_FN_SINPROD>, 8>(ctx, P, s);
+    case CQ_FN_COEF: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_COEF>>(ctx, P, s);
+    case CQ_FN_CONST: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_CONST>>(ctx, P, s);
+    case CQ_FN_AFFINE: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_AFFINE>>(ctx, P, s);
+    case CQ_FN_SINPROD: return launch_auto<FormTraits<FORM, DIM, DEG, BS, CQ_FN_SINPROD>>(ctx, P, s);
     default: set_error("unknown fn_kind %d", f.fn_kind); return CQ_ERR_INVALID;
   }
 }

@@ -17,6 +17,7 @@ class CSRMatrix:
         self._device_index = device_index
         self._stream_ptr = stream_ptr
         self.assembled = False
+        self.full_pattern = True  # pattern of every cell of the mesh (create_matrix(form))
 
     @property
     def size(self):

@@ -116,6 +116,11 @@ typedef struct cq_space {
   int64_t num_dofs;        /* scalar dofs; vector length = num_dofs * bs */
   const int32_t* dofmap;
   const double* coeffs;
+  /* Optional (may be NULL): scatter positions built once per (space, pattern) by
+   * cq_build_scatter_map -- the stand-in for the local-to-global map a PETSc Mat carries.
+   * With it cq_assemble_matrix runs the bulk-copy staged kernel and scatters without searching
+   * CSR rows; without it every (row, col) is found by binary search like MatSetValuesLocal. */
+  const uint8_t* elem_pos;
 } cq_space;
 
 /* One qr_data tuple (cells, qr_pts, qr_w[, qr_n]) (assemble_matrix.py:65-73) in ragged
@@ -171,6 +176,16 @@ int cq_assemble_vector(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
  * space may be NULL when the form has no coefficient. */
 int cq_assemble_scalar(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
                        const cq_space* space, const cq_quadrature* qr, double* m, void* stream);
+
+/* ---- scatter map (setup, not the timed path) -----------------------------------------------
+ * out [num_cells, cq_scatter_map_stride()] uint8: out[c*stride + i*n + j] = position of column
+ * dofmap[c,j] inside the sorted SCALAR row dofmap[c,i] (for bs > 1 the blocked position of
+ * component (a,a) is pos*bs + a in blocked row dofmap[c,i]*bs + a).  Rows longer than 255 scalar
+ * entries cannot be mapped: CQ_ERR_UNSUPPORTED (callers then leave elem_pos NULL).
+ * A is the pattern the matrices will use (values may be NULL). */
+int cq_scatter_map_stride(int cell_type, int degree);
+int cq_build_scatter_map(cq_ctx* ctx, int cell_type, int degree, int bs, int64_t num_cells,
+                         const int32_t* dofmap, const cq_csr* A, uint8_t* out, void* stream);
 
 /* ---- parity / debug hooks --------------------------------------------------------------- */
 /* call_basix for every point of `qr`: out [num_points, nbf] = D^alpha psi_j(xi_q) with

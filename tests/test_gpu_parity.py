@@ -102,8 +102,19 @@ def test_element_tensors_match_oracle(cuda_backend, tdim, degree, bs, distort):
         assert close(dev, ref), f"{name}: max rel {np.max(np.abs(dev - ref)) / np.max(np.abs(ref)):.3e}"
 
 
+@pytest.fixture(params=[1, 0], ids=["direct", "auto-staged"])
+def variant(request, cuda_backend):
+    """Both kernel families: 1 = direct-load kernel, 0 = auto (bulk-copy staged kernel wherever
+    it applies)."""
+    from customquad_b200.assemble import set_variant
+
+    set_variant(request.param)
+    yield request.param
+    set_variant(0)
+
+
 @pytest.mark.parametrize("tdim,degree,bs", SPACES)
-def test_assembly_matches_oracle(cuda_backend, oracle_backend, tdim, degree, bs):
+def test_assembly_matches_oracle(cuda_backend, oracle_backend, variant, tdim, degree, bs):
     """Full path: element kernels + scatter into CSR / vector / scalar, ragged rules, cell subset
     with repeats."""
     rng = np.random.default_rng(23)
@@ -166,6 +177,39 @@ def test_input_conventions(cuda_backend, oracle_backend):
     W2 = rng.random((5, 3))
     A = cuda_backend.matrix(forms.mass(V), [(cells, P2, W2)])
     assert close(A.data, oracle_backend.matrix(forms.mass(V), [(cells, P2, W2)]).data)
+
+
+def test_staged_kernel_stage_overflow_and_tails(cuda_backend, oracle_backend):
+    """Staged kernel corner cases: a rule far longer than a shared-memory stage (read from global
+    memory), an odd total point count (manual tail copy), many stages, zero-point entries."""
+    from customquad_b200.assemble import set_variant
+
+    set_variant(2)
+    try:
+        rng = np.random.default_rng(5)
+        for tdim in (2, 3):
+            mesh = make_mesh(tdim, True)
+            V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+            nq = rng.integers(0, 40, size=300)
+            nq[17] = 9001  # overflows any stage
+            nq[-1] = nq[-1] | 1
+            if nq.sum() % 2 == 0:
+                nq[-1] += 2
+                nq[5] += 1
+            assert nq.sum() % 2 == 1
+            cells = rng.integers(0, mesh.num_cells, size=300)
+            pts = [rng.random(tdim * n) for n in nq]
+            w = [rng.random(n) / max(n, 1) for n in nq]
+            nr = [rng.standard_normal(tdim * n) for n in nq]
+            for form in (forms.stiffness(V), forms.nitsche(V, 10.0)):
+                A, R = cuda_backend.matrix(form, [(cells, pts, w, nr)]), oracle_backend.matrix(form, [(cells, pts, w, nr)])
+                assert close(A.data, R.data)
+            lf = forms.load(V, cq.Analytic.sinprod(3.0))
+            assert close(cuda_backend.vector(lf, [(cells, pts, w)]), oracle_backend.vector(lf, [(cells, pts, w)]))
+            m, r = cuda_backend.scalar(forms.integral(mesh, 1.0), [(cells, pts, w)]), oracle_backend.scalar(forms.integral(mesh, 1.0), [(cells, pts, w)])
+            assert abs(m - r) <= RTOL * abs(r)
+    finally:
+        set_variant(0)
 
 
 def test_empty_and_degenerate(cuda_backend, oracle_backend):
