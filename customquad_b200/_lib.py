@@ -19,7 +19,7 @@ class FormDesc(C.Structure):
 
 
 class MeshDesc(C.Structure):
-    _fields_ = [("num_cells", C.c_int64), ("num_nodes", C.c_int64), ("geom_dofmap", C.c_void_p), ("coords", C.c_void_p)]
+    _fields_ = [("num_cells", C.c_int64), ("num_nodes", C.c_int64), ("geom_dofmap", C.c_void_p), ("coords", C.c_void_p), ("flags", C.c_int32)]
 
 
 class SpaceDesc(C.Structure):
@@ -57,6 +57,7 @@ _SIGNATURES = {
     "cq_assemble_matrix": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p]),
     "cq_assemble_vector": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+    "cq_mesh_classify": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(MeshDesc), C.POINTER(C.c_int32), C.c_void_p]),
     "cq_scatter_map_stride": (C.c_int, [C.c_int, C.c_int]),
     "cq_build_scatter_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_tabulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -42,10 +42,13 @@ def mesh_on_device(mesh, dev):
     """utils.get_vertices (utils.py:66-71) on the device."""
     torch = _torch()
     if dev not in mesh._dev:
-        mesh._dev[dev] = (
-            torch.from_numpy(np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)).to(dev),
-            torch.from_numpy(np.ascontiguousarray(mesh.geometry.x, dtype=np.float64)).to(dev),
-        )
+        gd = torch.from_numpy(np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)).to(dev)
+        xc = torch.from_numpy(np.ascontiguousarray(mesh.geometry.x, dtype=np.float64)).to(dev)
+        # setup-time classification: are all cells axis-aligned (constant diagonal Jacobian)?
+        flags = C.c_int32(0)
+        md = _lib.MeshDesc(mesh.num_cells, xc.shape[0], _ptr(gd), _ptr(xc), 0)
+        _lib.check(_lib.load().cq_mesh_classify(_lib.ctx(dev.index), int(mesh.cell_type), C.byref(md), C.byref(flags), _stream_ptr()))
+        mesh._dev[dev] = (gd, xc, int(flags.value))
     return mesh._dev[dev]
 
 
@@ -123,13 +126,14 @@ class _Call:
         gdim = mesh.geometry.dim
         self.q = normalise_qr(qr, gdim)
         q = self.q
-        if q.num_entries:
+        if q.num_entries and q._dev.get("checked_cells") != mesh.num_cells:  # validated once per rule
             assert int(q.cells.min()) >= 0 and int(q.cells.max()) < mesh.num_cells, "cell index out of range"
+            q._dev["checked_cells"] = mesh.num_cells
         if form.kind.name.startswith("NITSCHE"):
             assert q.n is not None, "this form needs normals: pass (cells, qr_pts, qr_w, qr_n)"
         self.keep = []
-        gd, xc = mesh_on_device(mesh, dev)
-        self.mesh = _lib.MeshDesc(mesh.num_cells, mesh.geometry.x.shape[0], _ptr(gd), _ptr(xc))
+        gd, xc, mflags = mesh_on_device(mesh, dev)
+        self.mesh = _lib.MeshDesc(mesh.num_cells, mesh.geometry.x.shape[0], _ptr(gd), _ptr(xc), mflags)
         self.V = form.function_spaces[0] if form.function_spaces else (form.coefficient.function_space if form.coefficient is not None else None)
         self.space = None
         if self.V is not None:

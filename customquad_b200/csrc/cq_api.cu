@@ -68,6 +68,7 @@ static int pack(cq_ctx* ctx, const cq_form_desc* f, const cq_mesh* mesh, const c
   P.err_flag = ctx->err_flag;
   P.elem_pos = space ? space->elem_pos : nullptr;
   P.work_counter = ctx->work_counter;
+  P.mesh_flags = mesh->flags;
   P.num_points = qr->num_points;
   P.bs = f->bs;
   for (int i = 0; i < f->nconsts; ++i) P.p[i] = f->consts[i];
@@ -90,6 +91,24 @@ __global__ void accumulate_rows_kernel(double* __restrict__ values, const int64_
     const int64_t dst = indptr[row0 + r], src = recv_indptr[r], n = recv_indptr[r + 1] - src;
     for (int64_t i = lane; i < n; i += 32) values[dst + i] += recv[src + i];
   }
+}
+
+// *flag &= (every cell has a constant, diagonal, non-singular Jacobian)
+template <int DIM>
+__global__ void classify_kernel(const KParams P, int64_t num_cells, int* flag) {
+  bool ok = true;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < num_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    double X[1 << DIM][DIM];
+    load_cell_vertices<DIM>(P, (int32_t)c, X);
+    CellGeom<DIM> geo;
+    geo.init(X, false);
+    ok = ok && geo.affine;
+#pragma unroll
+    for (int e = 0; e < DIM; ++e)
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) ok = ok && (k == e ? geo.c[1 << e][k] != 0.0 : geo.c[1 << e][k] == 0.0);
+  }
+  if (!ok) atomicAnd(flag, 0);
 }
 
 // scatter positions: one thread per (cell, i, j)
@@ -196,7 +215,7 @@ int cq_ctx_check(cq_ctx* ctx, void* stream) {
 int64_t cq_ctx_launch_count(const cq_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int cq_ctx_set_variant(cq_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 2) { set_error("bad variant"); return CQ_ERR_INVALID; }
+  if (!ctx || variant < 0 || variant > 3) { set_error("bad variant"); return CQ_ERR_INVALID; }
   ctx->variant = variant;
   return CQ_OK;
 }
@@ -253,6 +272,33 @@ int cq_element_tensors(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
     case 1: return launch_vector(ctx, *form, P, s);
     default: return launch_scalar(ctx, *form, P, s);
   }
+}
+
+int cq_mesh_classify(cq_ctx* ctx, int cell_type, const cq_mesh* mesh, int32_t* flags, void* stream) {
+  if (!ctx || !mesh || !flags || !mesh->geom_dofmap || !mesh->coords) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (cell_type != CQ_CELL_QUADRILATERAL && cell_type != CQ_CELL_HEXAHEDRON) { set_error("bad cell_type"); return CQ_ERR_UNSUPPORTED; }
+  *flags = 0;
+  if (mesh->num_cells <= 0) return CQ_OK;
+  if (!aligned(mesh->geom_dofmap, 16)) { set_error("geom_dofmap needs 16-B alignment"); return CQ_ERR_ALIGN; }
+  if (int rc = set_device(ctx)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  KParams P;
+  memset(&P, 0, sizeof P);
+  P.geom_dofmap = mesh->geom_dofmap;
+  P.coords = mesh->coords;
+  int one = 1;
+  // the error flag doubles as the scratch word (it is 0 between calls; restored below)
+  if (int rc = check_cuda(cudaMemcpyAsync(ctx->err_flag, &one, sizeof(int), cudaMemcpyHostToDevice, s), "flag init")) return rc;
+  const int grid = (int)((mesh->num_cells + 255) / 256 < (int64_t)ctx->num_sms * 8 ? (mesh->num_cells + 255) / 256 : (int64_t)ctx->num_sms * 8);
+  if (cell_type == CQ_CELL_QUADRILATERAL) classify_kernel<2><<<grid, 256, 0, s>>>(P, mesh->num_cells, ctx->err_flag);
+  else classify_kernel<3><<<grid, 256, 0, s>>>(P, mesh->num_cells, ctx->err_flag);
+  ctx->launches++;
+  if (int rc = check_cuda(cudaGetLastError(), "classify_kernel launch")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "flag D2H")) return rc;
+  if (int rc = check_cuda(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s), "flag reset")) return rc;
+  if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
+  if (*ctx->host_flag) *flags |= CQ_MESH_AXIS_ALIGNED;
+  return CQ_OK;
 }
 
 int cq_scatter_map_stride(int cell_type, int degree) {

@@ -99,6 +99,12 @@ struct CellGeom {
   static constexpr int NV = 1 << DIM;
   double c[NV][DIM];  // c[m][component]
   double hK;          // ufl.CellDiameter: largest vertex-vertex distance (demo/poisson.py:143)
+  // Affine cell (all multilinear coefficients of order >= 2 are exactly zero, as for every cell of
+  // a create_rectangle / create_box mesh): J is the same at every point, so J, det J and adj J are
+  // evaluated once per cell (init_affine) instead of once per point.  Same numbers: the per-point
+  // formula reduces to J[k][e] = c[1<<e][k] when the higher coefficients vanish.
+  bool affine;
+  double det0, inv_det0, adj0[DIM][DIM];
 
   // X[v][comp] with v in the points' frame lattice order of Lattice<DIM,1>
   CQ_DEVINL void init(const double (&X)[NV][DIM], bool need_h) {
@@ -127,6 +133,12 @@ struct CellGeom {
 #pragma unroll
       for (int m = 0; m < NV; ++m) c[m][k] = tmp[m];
     }
+    affine = true;
+#pragma unroll
+    for (int m = 0; m < NV; ++m)
+      if ((m & (m - 1)) != 0)  // more than one bit set: bilinear / trilinear terms
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) affine = affine && (c[m][k] == 0.0);
     hK = 0.0;
     if (need_h) {
       double h2 = 0.0;
@@ -200,6 +212,20 @@ CQ_DEVINL double det_adj(const double (&J)[DIM][DIM], double (&adj)[DIM][DIM]) {
     adj[1][2] = fma(J[0][2], J[1][0], -J[0][0] * J[1][2]);
     adj[2][2] = fma(J[0][0], J[1][1], -J[0][1] * J[1][0]);
     return fma(J[0][0], adj[0][0], fma(J[0][1], adj[1][0], J[0][2] * adj[2][0]));
+  }
+}
+
+// per-cell constants of an affine cell (CellGeom::affine): det J, 1/det J, adj J
+template <int DIM>
+CQ_DEVINL void init_affine(CellGeom<DIM>& geo) {
+  if (geo.affine) {
+    double J[DIM][DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k)
+#pragma unroll
+      for (int e = 0; e < DIM; ++e) J[k][e] = geo.c[1 << e][k];
+    geo.det0 = det_adj<DIM>(J, geo.adj0);
+    geo.inv_det0 = 1.0 / geo.det0;
   }
 }
 

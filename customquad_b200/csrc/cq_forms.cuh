@@ -87,11 +87,27 @@ CQ_DEVINL void accumulate_point(double (&acc)[T::NACC], const CellGeom<T::DIM>& 
   double psi[N], g[N][DIM];
   tabulate_point<DIM, T::DEG, T::NEED_PSI, T::NEED_GRAD>(xi, psi, g);
 
-  double J[DIM][DIM], adj[DIM][DIM];
-  geo.jacobian(xi, J);
-  double det;
-  if constexpr (T::NEED_GRAD) det = det_adj<DIM>(J, adj);
-  else det = det_only<DIM>(J);
+  double adj[DIM][DIM], det, inv_det;
+  if (geo.affine) {  // constant Jacobian: per-cell values (warp-uniform for tensor meshes)
+    det = geo.det0;
+    inv_det = geo.inv_det0;
+    if constexpr (T::NEED_GRAD) {
+#pragma unroll
+      for (int e = 0; e < DIM; ++e)
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) adj[e][k] = geo.adj0[e][k];
+    }
+  } else {
+    double J[DIM][DIM];
+    geo.jacobian(xi, J);
+    if constexpr (T::NEED_GRAD) {
+      det = det_adj<DIM>(J, adj);
+      inv_det = 1.0 / det;
+    } else {
+      det = det_only<DIM>(J);
+      inv_det = 0.0;
+    }
+  }
   const double adet = fabs(det);
   const double s = w * adet;  // w_q |det J_q|
 
@@ -104,7 +120,7 @@ CQ_DEVINL void accumulate_point(double (&acc)[T::NACC], const CellGeom<T::DIM>& 
     }
   } else if constexpr (T::FORM_ID == CQ_FORM_STIFFNESS) {
     // s G_i.G_j = (w/|det|) (adj^T g_i).(adj^T g_j),  G = adj^T g / det
-    const double sc = w / adet;
+    const double sc = w * fabs(inv_det);
     double a[N][DIM];
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -130,7 +146,6 @@ CQ_DEVINL void accumulate_point(double (&acc)[T::NACC], const CellGeom<T::DIM>& 
     }
   } else {
     // ---- everything that may need n.grad(psi_i), coefficient values, closed-form data --------
-    const double inv_det = T::NEED_GRAD ? 1.0 / det : 0.0;
     double dn[N];  // n . grad psi_i  (physical)
     if constexpr (T::NEED_NORMAL) {
       double m[DIM];  // m_e = sum_k adj[e][k] n_k / det

@@ -34,6 +34,7 @@ struct KParams {
   unsigned int* work_counter;            // ctx-owned, zeroed before a staged launch
   int64_t num_points;                    // length of pts / w (bulk-copy tail handling)
   int stage_points;                      // points capacity of one smem stage
+  int mesh_flags;                        // cq_mesh.flags
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)
   int elem_out;    // 1: write un-scattered element tensors to out[k, :]
   double betaN;
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(THREADS) assemble_direct_kernel(const KParams 
       load_cell_vertices<DIM>(P, cell, X);
       CellGeom<DIM> geo;
       geo.init(X, T::NEED_H);
+      init_affine<DIM>(geo);
       const double gamma = T::NEED_H ? P.betaN / geo.hK : 0.0;
       const double* coef = nullptr;
       double coef_reg[T::NEED_COEF && T::NCOEF <= 32 ? T::NCOEF : 1];

@@ -2,7 +2,7 @@
 // (grid-strided) kernel and the bulk-copy staged persistent kernel, and the choice between them.
 #pragma once
 #include "cq_internal.h"
-#include "cq_staged.cuh"
+#include "cq_staged_kernel.cuh"
 
 namespace cq {
 
@@ -27,11 +27,11 @@ static bool staged_ok(const cq_ctx* ctx, const KParams& P) {
   return true;
 }
 
-template <class T, int G, int NPW, int NCW>
+template <class T, int G, int NPW, int NCW, int MODE = 0>
 static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   constexpr int CB = 32;
   using Lay = StagedLayout<T, CB>;
-  auto kernel = assemble_staged_kernel<T, G, NPW, NCW>;
+  auto kernel = assemble_staged_kernel<T, G, NPW, NCW, MODE>;
   // stage capacity: ~1.25x the mean points of 32 entries, bounded by the shared memory per SM
   const size_t budget = (size_t)ctx->max_smem_optin - 1024;
   const size_t per_point = (size_t)T::DIM * 8 * (T::NEED_NORMAL ? 2 : 1) + 8;
@@ -65,10 +65,19 @@ struct StagedShape {
   static constexpr int G = T::NACC <= 16 ? 4 : 8;
 };
 
+// mesh flags (cq_mesh.flags)
+constexpr int MESH_AXIS_ALIGNED = 1;
+
 template <class T, int GDIRECT = 8>
 static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
   using S = StagedShape<T>;
-  if (staged_ok<T>(ctx, P)) return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
+  if (staged_ok<T>(ctx, P)) {
+    // mass / stiffness on quadrilaterals whose Jacobian is constant and diagonal: moment kernel
+    if constexpr (T::DIM == 2 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {
+      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) return launch_staged<T, 1, 4, 4, 1>(ctx, P, s);
+    }
+    return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
+  }
   if (ctx->variant == 2) { set_error("staged kernel requested but not applicable (scatter map / alignment / element output)"); return CQ_ERR_UNSUPPORTED; }
   return launch_direct<T, GDIRECT>(ctx, P, s);
 }

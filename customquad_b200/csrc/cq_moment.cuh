@@ -1,0 +1,180 @@
+// cq_moment.cuh -- mass / stiffness matrices on axis-aligned quadrilateral cells through the
+// monomial moments of the runtime quadrature rule.
+//
+// On a cell whose Jacobian is constant and diagonal (every cell of a dolfinx create_rectangle
+// mesh: J = diag(hx, hy)), the integrands of the reference's bilinear forms are polynomials in
+// the reference coordinate with per-cell constant coefficients:
+//
+//   mass       A_ij = |det J| sum_q w_q psi_i psi_j
+//   stiffness  A_ij = sum_k (|det J| / J_kk^2) sum_q w_q d_k psi_i d_k psi_j
+//
+// and psi_i = l_a0(xi0) l_a1(xi1).  Each product l_a l_c (or l_a' l_c') is a polynomial of degree
+// <= 2 deg in one variable, so every entry is a fixed linear combination of the (2 deg + 1)^2
+// moments  mu[p][q] = sum_q w_q t0^p t1^q,  t = xi - 1/2  (centred monomials keep the combination
+// well conditioned: measured max deviation from the direct evaluation 2.5e-15 of max|A| for Q2).
+// Per point this costs 15 (Q1) / 37 (Q2) FP64 instructions instead of ~65 / ~190, which moves the
+// Q1 AND the Q2 kernels from the FP64 roofline to the HBM roofline.  The reference computes the
+// same sums entry by entry (README.md:133-158 generated kernel); results agree to FP64 rounding.
+//
+// One thread per qr entry (no cross-lane reduction at all); the points come from the staged
+// shared-memory slice, so the per-thread streams cost no coalescing.  After the point loop the
+// thread expands its moments into the n x n element tensor and scatters each value as soon as it
+// is formed (no n x n register tile): for every unordered x-pair (a0 <= c0) contract mu with the
+// x coefficient rows once, then for every ordered y-pair contract with the y rows.
+#pragma once
+#include <utility>
+
+#include "cq_staged.cuh"
+
+namespace cq {
+
+template <int B, int E, class F>
+CQ_DEVINL void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(static_cast<F&&>(f));
+  }
+}
+
+// 1-D Lagrange basis in the centred variable t = xi - 1/2 and the coefficient rows of pair products
+template <int DEG>
+struct Poly1D {
+  static constexpr int P = 2 * DEG + 1;
+  // coefficient of t^u in l_a(t + 1/2)  (a = lattice coordinate 0..DEG)
+  CQ_HD static constexpr double L(int a, int u) {
+    if (DEG == 1) {
+      constexpr double T[2][2] = {{0.5, -1.0}, {0.5, 1.0}};
+      return u < 2 ? T[a][u] : 0.0;
+    } else {
+      // l_0 = 2t^2 - t, l_1 = 1 - 4t^2 (midpoint), l_2 = 2t^2 + t
+      constexpr double T[3][3] = {{0.0, -1.0, 2.0}, {1.0, 0.0, -4.0}, {0.0, 1.0, 2.0}};
+      return u < 3 ? T[a][u] : 0.0;
+    }
+  }
+  CQ_HD static constexpr double dL(int a, int u) { return u < DEG ? (u + 1) * L(a, u + 1) : 0.0; }
+  CQ_HD static constexpr double R00(int a, int c, int p) {
+    double s = 0.0;
+    for (int u = 0; u <= DEG; ++u)
+      if (p - u >= 0 && p - u <= DEG) s += L(a, u) * L(c, p - u);
+    return s;
+  }
+  CQ_HD static constexpr double R11(int a, int c, int p) {
+    double s = 0.0;
+    for (int u = 0; u < DEG; ++u)
+      if (p - u >= 0 && p - u < DEG) s += dL(a, u) * dL(c, p - u);
+    return s;
+  }
+};
+
+// local dof of lattice point (a0, a1)
+template <int DEG>
+CQ_HD constexpr int quad_dof_of(int a0, int a1) {
+  for (int j = 0; j < Lattice<2, DEG>::N; ++j)
+    if (Lattice<2, DEG>::t(j, 0) == a0 && Lattice<2, DEG>::t(j, 1) == a1) return j;
+  return -1;
+}
+
+template <class T, int CB>
+CQ_DEVINL void scatter_value(const KParams& P, const StageMeta<T, CB>& M, const int e, const int i, const int j, const double v) {
+  constexpr int N = T::N;
+  const int pij = M.pos[e][i * N + j];
+  const long long si = M.rowstart[i][e];
+  const int bs = P.bs;
+  if (bs == 1) {
+    red_add_f64(P.values + si + pij, v);
+  } else {
+    const int li = M.rowlen[i][e];
+    for (int a = 0; a < bs; ++a) red_add_f64(P.values + si + (long long)a * li + pij * bs + a, v);
+  }
+}
+
+// T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}
+template <class T, int CB>
+CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active) {
+  constexpr int DEG = T::DEG;
+  using Q = Poly1D<DEG>;
+  constexpr int Pn = Q::P;
+  constexpr bool STIFF = T::FORM_ID == CQ_FORM_STIFFNESS;
+  double mu[Pn][Pn];
+#pragma unroll
+  for (int p = 0; p < Pn; ++p)
+#pragma unroll
+    for (int q = 0; q < Pn; ++q) mu[p][q] = 0.0;
+  const int nq = active ? M.nq[e] : 0;
+  const double* pp = M.pts[e];
+  const double* wp = M.w[e];
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    const double2 xy = *reinterpret_cast<const double2*>(pp + 2 * q);
+    const double w = wp[q];
+    const double tx = xy.x - 0.5, ty = xy.y - 0.5;
+    double X[Pn], WY[Pn];
+    X[0] = 1.0; X[1] = tx;
+    WY[0] = w; WY[1] = w * ty;
+#pragma unroll
+    for (int p = 2; p < Pn; ++p) {
+      X[p] = X[p - 1] * tx;
+      WY[p] = WY[p - 1] * ty;
+    }
+#pragma unroll
+    for (int q2 = 0; q2 < Pn; ++q2) mu[0][q2] += WY[q2];
+#pragma unroll
+    for (int p = 1; p < Pn; ++p)
+#pragma unroll
+      for (int q2 = 0; q2 < Pn; ++q2) mu[p][q2] = fma(X[p], WY[q2], mu[p][q2]);
+  }
+  if (!active) return;
+  // per-cell constants: J = diag(J00, J11) (axis-aligned cell; checked for the whole mesh at setup)
+  const double J00 = M.X[2 * 2 + 0][e] - M.X[0][e];  // local vertex 2 is the +x neighbour (Lattice<2,1>)
+  const double J11 = M.X[1 * 2 + 1][e] - M.X[1][e];  // local vertex 1 is the +y neighbour
+  const double adet = fabs(J00 * J11);
+  const double k0 = STIFF ? fabs(J11 / J00) : adet;   // stiffness: |det|/J00^2 ; mass: |det|
+  const double k1 = STIFF ? fabs(J00 / J11) : 0.0;    // stiffness: |det|/J11^2
+
+  static_for<0, DEG + 1>([&](auto A0) {
+    static_for<decltype(A0)::value, DEG + 1>([&](auto C0) {
+      constexpr int a0 = decltype(A0)::value, c0 = decltype(C0)::value;
+      // contract the x index:  U0[q] = sum_p R00x[p] mu[p][q],  U1[q] = sum_p R11x[p] mu[p][q]
+      double U0[Pn], U1[Pn];
+#pragma unroll
+      for (int q = 0; q < Pn; ++q) U0[q] = U1[q] = 0.0;
+      static_for<0, Pn>([&](auto PP) {
+        constexpr int p = decltype(PP)::value;
+        constexpr double r00 = Q::R00(a0, c0, p), r11 = Q::R11(a0, c0, p);
+        if constexpr (r00 != 0.0) {
+#pragma unroll
+          for (int q = 0; q < Pn; ++q) U0[q] = fma(r00, mu[p][q], U0[q]);
+        }
+        if constexpr (STIFF && r11 != 0.0) {
+#pragma unroll
+          for (int q = 0; q < Pn; ++q) U1[q] = fma(r11, mu[p][q], U1[q]);
+        }
+      });
+      static_for<0, DEG + 1>([&](auto A1) {
+        static_for<0, DEG + 1>([&](auto C1) {
+          constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
+          double m0 = 0.0, m1 = 0.0;  // y contractions
+          static_for<0, Pn>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            constexpr double r00 = Q::R00(a1, c1, q), r11 = Q::R11(a1, c1, q);
+            if constexpr (STIFF) {
+              if constexpr (r00 != 0.0) m0 = fma(r00, U1[q], m0);  // d/dx d/dx: R11 in x, R00 in y
+              if constexpr (r11 != 0.0) m1 = fma(r11, U0[q], m1);  // d/dy d/dy: R00 in x, R11 in y
+            } else {
+              if constexpr (r00 != 0.0) m0 = fma(r00, U0[q], m0);
+            }
+          });
+          const double v = STIFF ? fma(k0, m0, k1 * m1) : k0 * m0;
+          constexpr int i = quad_dof_of<DEG>(a0, a1), j = quad_dof_of<DEG>(c0, c1);
+          scatter_value<T, CB>(P, M, e, i, j, v);
+          if constexpr (a0 != c0) {  // x-swapped entry has the same value (the x rows are symmetric)
+            constexpr int i2 = quad_dof_of<DEG>(c0, a1), j2 = quad_dof_of<DEG>(a0, c1);
+            scatter_value<T, CB>(P, M, e, i2, j2, v);
+          }
+        });
+      });
+    });
+  });
+}
+
+}  // namespace cq

@@ -108,6 +108,7 @@ CQ_DEVINL void staged_process_entry(const KParams& P, const StageMeta<T, CB>& M,
       for (int k = 0; k < DIM; ++k) X[v][k] = M.X[v * DIM + k][e];
     CellGeom<DIM> geo;
     geo.init(X, T::NEED_H);
+    init_affine<DIM>(geo);
     const double gamma = T::NEED_H ? P.betaN / geo.hK : 0.0;
     double coef_reg[T::NEED_COEF ? T::NCOEF : 1];
     if constexpr (T::NEED_COEF) {
@@ -181,199 +182,6 @@ CQ_DEVINL void staged_process_entry(const KParams& P, const StageMeta<T, CB>& M,
       }
     }
   }
-}
-
-// ---- the kernel ------------------------------------------------------------------------------------------
-template <class T, int G, int NPW, int NCW>
-__global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(const KParams P) {
-  constexpr int CB = 32;
-  constexpr int DIM = T::DIM, N = T::N, NV = T::NV;
-  using Meta = StageMeta<T, CB>;
-  using Lay = StagedLayout<T, CB>;
-  constexpr int CPW = 32 / G;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t full_bar[NPW], empty_bar[NPW];
-  const int PB = P.stage_points;
-  const size_t stage_bytes = Lay::stage_bytes(PB);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < NPW; ++s) {
-      mbar_init(&full_bar[s], 2);     // producer lane 0 twice: expect_tx at copy issue, arrive after the header
-      mbar_init(&empty_bar[s], NCW);  // one elected lane per consumer warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
-  double msum = 0.0;
-
-  if (warp < NPW) {
-    // =========================== producer warp: owns stage `warp` ===========================
-    unsigned char* base = smem_raw + (size_t)warp * stage_bytes;
-    Meta& M = *reinterpret_cast<Meta*>(base);
-    double* s_pts = reinterpret_cast<double*>(base + Lay::meta_bytes);
-    double* s_w = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB));
-    double* s_nrm = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB) + Lay::w_bytes(PB));
-    uint32_t parity = 0;
-    for (int it = 0;; ++it) {
-      if (it > 0) {
-        mbar_wait(&empty_bar[warp], parity);
-        parity ^= 1;
-      }
-      long long t = 0;
-      if (lane == 0) t = atomicAdd(P.work_counter, 1u);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= num_stages) {
-        if (lane == 0) {
-          M.nent = -1;
-          mbar_arrive(&full_bar[warp]);
-          mbar_arrive(&full_bar[warp]);
-        }
-        break;
-      }
-      const int64_t k0 = t * CB;
-      const int nent = (int)((P.num_entries - k0) < CB ? (P.num_entries - k0) : CB);
-      const bool valid = lane < nent;
-      const int64_t k = k0 + (valid ? lane : nent - 1);
-      const int64_t o0 = __ldg(P.offsets + k), o1 = __ldg(P.offsets + k + 1);
-      const int32_t cell = __ldg(P.cells + k);
-      const int64_t P0 = __shfl_sync(0xffffffffu, o0, 0);
-      const int64_t P1 = __shfl_sync(0xffffffffu, o1, nent - 1);
-      const int64_t Pa = P0 & ~(int64_t)1;  // even start: 16-B aligned for 8 / 16 / 24-byte strides
-      // ---- bulk copies of the staged prefix [Pa, Pa + cnt) --------------------------------------
-      int64_t cnt = P1 - Pa;
-      if (cnt > PB) cnt = PB & ~1;          // overflow: the tail entries read global memory directly
-      int64_t cnt_copy = (cnt + 1) & ~(int64_t)1;
-      int tail = 0;                          // one odd point at the very end of the arrays
-      if (Pa + cnt_copy > P.num_points) { cnt_copy = cnt - 1; tail = 1; }
-      if (lane == 0) {
-        const uint32_t b_pts = (uint32_t)(cnt_copy * DIM * 8), b_w = (uint32_t)(cnt_copy * 8);
-        mbar_arrive_expect_tx(&full_bar[warp], b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w);
-        if (cnt_copy > 0) {
-          bulk_g2s(s_pts, P.pts + Pa * DIM, b_pts, &full_bar[warp]);
-          bulk_g2s(s_w, P.w + Pa, b_w, &full_bar[warp]);
-          if constexpr (T::NEED_NORMAL) bulk_g2s(s_nrm, P.normals + Pa * DIM, b_pts, &full_bar[warp]);
-        }
-        if (tail) {
-          const int64_t q = Pa + cnt - 1, l = cnt - 1;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) {
-            s_pts[l * DIM + d] = __ldg(P.pts + q * DIM + d);
-            if constexpr (T::NEED_NORMAL) s_nrm[l * DIM + d] = __ldg(P.normals + q * DIM + d);
-          }
-          s_w[l] = __ldg(P.w + q);
-        }
-      }
-      // ---- per-entry header, one lane per entry ------------------------------------------------
-      const int nq = valid ? (int)(o1 - o0) : 0;
-      const bool staged = (o1 - Pa) <= cnt;
-      M.nq[lane] = nq;
-      M.cell[lane] = cell;
-      M.pts[lane] = staged ? s_pts + (o0 - Pa) * DIM : P.pts + o0 * DIM;
-      M.w[lane] = staged ? s_w + (o0 - Pa) : P.w + o0;
-      if constexpr (T::NEED_NORMAL) M.nrm[lane] = staged ? s_nrm + (o0 - Pa) * DIM : P.normals + o0 * DIM;
-      if (valid) {
-        int32_t vid[NV];
-        if constexpr (DIM == 2) {
-          const int4 v = __ldg(reinterpret_cast<const int4*>(P.geom_dofmap) + cell);
-          vid[0] = v.x; vid[1] = v.y; vid[2] = v.z; vid[3] = v.w;
-        } else {
-          const int4 v0 = __ldg(reinterpret_cast<const int4*>(P.geom_dofmap) + 2 * (int64_t)cell);
-          const int4 v1 = __ldg(reinterpret_cast<const int4*>(P.geom_dofmap) + 2 * (int64_t)cell + 1);
-          vid[0] = v0.x; vid[1] = v0.y; vid[2] = v0.z; vid[3] = v0.w;
-          vid[4] = v1.x; vid[5] = v1.y; vid[6] = v1.z; vid[7] = v1.w;
-        }
-        int32_t dof[T::RANK >= 1 ? N : 1];
-        if constexpr (T::RANK >= 1) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) dof[i] = __ldg(P.dofmap + (int64_t)cell * N + i);
-        }
-        if constexpr (Meta::MAT) {
-          const int4* src = reinterpret_cast<const int4*>(P.elem_pos + (int64_t)cell * Meta::NPOS);
-          int4* dst = reinterpret_cast<int4*>(&M.pos[lane][0]);
-#pragma unroll
-          for (int i = 0; i < Meta::NPOS / 16; ++i) dst[i] = __ldg(src + i);
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) M.X[v * DIM + d][lane] = __ldg(P.coords + 3 * (int64_t)vid[v] + d);
-        if constexpr (Meta::MAT) {
-          const int bs = P.bs;
-#pragma unroll
-          for (int i = 0; i < N; ++i) {
-            const long long rs = __ldg(P.indptr + (int64_t)dof[i] * bs);
-            M.rowstart[i][lane] = rs;
-            M.rowlen[i][lane] = bs == 1 ? 0 : (int)(__ldg(P.indptr + (int64_t)dof[i] * bs + 1) - rs);
-          }
-        }
-        if constexpr (Meta::VEC) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) M.dofs[i][lane] = dof[i];
-        }
-        if constexpr (T::NEED_COEF) {
-          const double* c = P.coeffs + (int64_t)cell * T::NCOEF;
-#pragma unroll
-          for (int i = 0; i < T::NCOEF; ++i) M.coef[i][lane] = __ldg(c + i);
-        }
-      }
-      // ---- sort entries by trip count, longest first (bitonic over the 32 lanes) ----------------
-      int key = (((nq + G - 1) / G) << 5) | (31 - lane);  // ties: lower lane first
-#pragma unroll
-      for (int size = 2; size <= 32; size <<= 1)
-#pragma unroll
-        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-          const int other = __shfl_xor_sync(0xffffffffu, key, stride);
-          const bool desc = (lane & size) == 0;  // final order: descending across lanes
-          const bool lower = (lane & stride) == 0;
-          const int mx = key > other ? key : other, mn = key > other ? other : key;
-          key = (desc == lower) ? mx : mn;
-        }
-      M.order[lane] = 31 - (key & 31);
-      if (lane == 0) {
-        M.nent = nent;
-        M.next = 0;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[warp]);  // release: header + tail stores are visible
-    }
-  } else {
-    // =========================== consumer warps ===========================================
-    const int r = lane & (G - 1), grp = lane / G;
-    uint32_t ended = 0, parity = 0;
-    int s = 0;
-    while (ended != (1u << NPW) - 1u) {
-      if (!((ended >> s) & 1u)) {
-        mbar_wait(&full_bar[s], parity);
-        Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
-        const int nent = M.nent;
-        if (nent < 0) {
-          ended |= 1u << s;
-        } else {
-          for (;;) {
-            int e0 = 0;
-            if (lane == 0) e0 = atomicAdd(&M.next, CPW);
-            e0 = __shfl_sync(0xffffffffu, e0, 0);
-            if (e0 >= nent) break;
-            const bool active = e0 + grp < nent;
-            const int e = active ? M.order[e0 + grp] : 0;
-            staged_process_entry<T, G, CB>(P, M, e, active, r, msum);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[s]);
-        }
-      }
-      if (++s == NPW) {
-        s = 0;
-        parity ^= 1;
-      }
-    }
-  }
-  if constexpr (T::RANK == 0) block_sum_atomic(msum, P.out);
 }
 
 }  // namespace cq

@@ -1,0 +1,261 @@
+// cq_staged_kernel.cuh -- the staged persistent kernel (producer / consumer roles); see cq_staged.cuh
+#pragma once
+#include "cq_moment.cuh"
+#include "cq_staged.cuh"
+
+namespace cq {
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+// MODE 0: G lanes per entry accumulate the element tensor point by point (any form, any cell).
+// MODE 1: one thread per entry, monomial moments (cq_moment.cuh; G must be 1).
+template <class T, int G, int NPW, int NCW, int MODE>
+__global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(const KParams P) {
+  constexpr int CB = 32;
+  constexpr int DIM = T::DIM, N = T::N, NV = T::NV;
+  using Meta = StageMeta<T, CB>;
+  using Lay = StagedLayout<T, CB>;
+  constexpr int CPW = 32 / G;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[NPW], empty_bar[NPW];
+  const int PB = P.stage_points;
+  const size_t stage_bytes = Lay::stage_bytes(PB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NPW; ++s) {
+      mbar_init(&full_bar[s], 2);     // producer lane 0 twice: expect_tx at copy issue, arrive after the header
+      mbar_init(&empty_bar[s], NCW);  // one elected lane per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
+  double msum = 0.0;
+
+  if (warp < NPW) {
+    // =========================== producer warp: owns stage `warp` ===========================
+    // Filling a stage is a chain of dependent global loads (work counter -> offsets, cell ids ->
+    // dofmap rows -> vertex coordinates, CSR row starts): ~4 round trips.  The chain is software-
+    // pipelined over three stages held in registers -- while stage A is being published, level 3
+    // of stage B, level 2 of stage C and level 1 of stage D are in flight -- so a free slot only
+    // waits for its bulk copy.
+    unsigned char* base = smem_raw + (size_t)warp * stage_bytes;
+    Meta& M = *reinterpret_cast<Meta*>(base);
+    double* s_pts = reinterpret_cast<double*>(base + Lay::meta_bytes);
+    double* s_w = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB));
+    double* s_nrm = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB) + Lay::w_bytes(PB));
+    constexpr int NP16 = Meta::MAT ? Meta::NPOS / 16 : 1;
+    struct Regs {
+      long long t;  // stage index; -2: pipeline bubble, -1: no more work
+      int nent;
+      bool valid;
+      int64_t o0, o1;
+      int32_t cell;
+      int32_t vid[NV];
+      int32_t dof[T::RANK >= 1 ? N : 1];
+      int4 pos[NP16];
+      double X[NV * DIM];
+      long long rs[Meta::MAT ? N : 1];
+      int rl[Meta::MAT ? N : 1];
+    };
+    Regs ra, rb, rc;
+    ra.t = rb.t = rc.t = -2;
+    ra.valid = rb.valid = rc.valid = false;
+    auto grab = [&]() -> long long {
+      long long t = 0;
+      if (lane == 0) t = atomicAdd(P.work_counter, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      return t < num_stages ? t : -1;
+    };
+    long long td = grab();
+    uint32_t parity = 0;
+    bool first = true;
+    for (;;) {
+      // ---------------- publish stage A ----------------
+      if (ra.t == -1) {
+        if (!first) mbar_wait(&empty_bar[warp], parity);
+        if (lane == 0) {
+          M.nent = -1;
+          mbar_arrive(&full_bar[warp]);
+          mbar_arrive(&full_bar[warp]);
+        }
+        break;
+      }
+      if (ra.t >= 0) {
+        if (!first) {
+          mbar_wait(&empty_bar[warp], parity);
+          parity ^= 1;
+        }
+        first = false;
+        const int nent = ra.nent;
+        const int64_t o0 = ra.o0, o1 = ra.o1;
+        const int64_t P0 = __shfl_sync(0xffffffffu, o0, 0);
+        const int64_t P1 = __shfl_sync(0xffffffffu, o1, nent - 1);
+        const int64_t Pa = P0 & ~(int64_t)1;  // even start: 16-B aligned for 8 / 16 / 24-byte strides
+        int64_t cnt = P1 - Pa;
+        if (cnt > PB) cnt = PB & ~1;          // overflow: the tail entries read global memory directly
+        int64_t cnt_copy = (cnt + 1) & ~(int64_t)1;
+        int tail = 0;                          // one odd point at the very end of the arrays
+        if (Pa + cnt_copy > P.num_points) { cnt_copy = cnt - 1; tail = 1; }
+        if (lane == 0) {
+          const uint32_t b_pts = (uint32_t)(cnt_copy * DIM * 8), b_w = (uint32_t)(cnt_copy * 8);
+          mbar_arrive_expect_tx(&full_bar[warp], b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w);
+          if (cnt_copy > 0) {
+            bulk_g2s(s_pts, P.pts + Pa * DIM, b_pts, &full_bar[warp]);
+            bulk_g2s(s_w, P.w + Pa, b_w, &full_bar[warp]);
+            if constexpr (T::NEED_NORMAL) bulk_g2s(s_nrm, P.normals + Pa * DIM, b_pts, &full_bar[warp]);
+          }
+          if (tail) {
+            const int64_t q = Pa + cnt - 1, l = cnt - 1;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+              s_pts[l * DIM + d] = __ldg(P.pts + q * DIM + d);
+              if constexpr (T::NEED_NORMAL) s_nrm[l * DIM + d] = __ldg(P.normals + q * DIM + d);
+            }
+            s_w[l] = __ldg(P.w + q);
+          }
+        }
+        const int nq = ra.valid ? (int)(o1 - o0) : 0;
+        const bool staged = (o1 - Pa) <= cnt;
+        M.nq[lane] = nq;
+        M.cell[lane] = ra.cell;
+        M.pts[lane] = staged ? s_pts + (o0 - Pa) * DIM : P.pts + o0 * DIM;
+        M.w[lane] = staged ? s_w + (o0 - Pa) : P.w + o0;
+        if constexpr (T::NEED_NORMAL) M.nrm[lane] = staged ? s_nrm + (o0 - Pa) * DIM : P.normals + o0 * DIM;
+        if (ra.valid) {
+          if constexpr (Meta::MAT) {
+            int4* dst = reinterpret_cast<int4*>(&M.pos[lane][0]);
+#pragma unroll
+            for (int i = 0; i < NP16; ++i) dst[i] = ra.pos[i];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              M.rowstart[i][lane] = ra.rs[i];
+              M.rowlen[i][lane] = ra.rl[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NV * DIM; ++i) M.X[i][lane] = ra.X[i];
+          if constexpr (Meta::VEC) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) M.dofs[i][lane] = ra.dof[i];
+          }
+          if constexpr (T::NEED_COEF) {
+            const double* c = P.coeffs + (int64_t)ra.cell * T::NCOEF;
+#pragma unroll
+            for (int i = 0; i < T::NCOEF; ++i) M.coef[i][lane] = __ldg(c + i);
+          }
+        }
+        // sort entries by trip count, longest first (bitonic over the 32 lanes)
+        int key = (((nq + G - 1) / G) << 5) | (31 - lane);  // ties: lower lane first
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+          for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            const int other = __shfl_xor_sync(0xffffffffu, key, stride);
+            const bool desc = (lane & size) == 0;
+            const bool lower = (lane & stride) == 0;
+            const int mx = key > other ? key : other, mn = key > other ? other : key;
+            key = (desc == lower) ? mx : mn;
+          }
+        M.order[lane] = 31 - (key & 31);
+        if (lane == 0) {
+          M.nent = nent;
+          M.next = 0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[warp]);  // release: header + tail stores are visible
+      }
+      // ---------------- advance the pipeline: A <- B (+ level 3), B <- C (+ level 2), C <- D (+ level 1) ----
+      ra = rb;
+      if (ra.t >= 0 && ra.valid) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) ra.X[v * DIM + d] = __ldg(P.coords + 3 * (int64_t)ra.vid[v] + d);
+        if constexpr (Meta::MAT) {
+          const int bs = P.bs;
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const long long rs = __ldg(P.indptr + (int64_t)ra.dof[i] * bs);
+            ra.rs[i] = rs;
+            ra.rl[i] = bs == 1 ? 0 : (int)(__ldg(P.indptr + (int64_t)ra.dof[i] * bs + 1) - rs);
+          }
+        }
+      }
+      rb = rc;
+      if (rb.t >= 0 && rb.valid) {
+        const int32_t cell = rb.cell;
+        if constexpr (DIM == 2) {
+          const int4 v = __ldg(reinterpret_cast<const int4*>(P.geom_dofmap) + cell);
+          rb.vid[0] = v.x; rb.vid[1] = v.y; rb.vid[2] = v.z; rb.vid[3] = v.w;
+        } else {
+          const int4 v0 = __ldg(reinterpret_cast<const int4*>(P.geom_dofmap) + 2 * (int64_t)cell);
+          const int4 v1 = __ldg(reinterpret_cast<const int4*>(P.geom_dofmap) + 2 * (int64_t)cell + 1);
+          rb.vid[0] = v0.x; rb.vid[1] = v0.y; rb.vid[2] = v0.z; rb.vid[3] = v0.w;
+          rb.vid[4] = v1.x; rb.vid[5] = v1.y; rb.vid[6] = v1.z; rb.vid[7] = v1.w;
+        }
+        if constexpr (T::RANK >= 1) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) rb.dof[i] = __ldg(P.dofmap + (int64_t)cell * N + i);
+        }
+        if constexpr (Meta::MAT) {
+          const int4* src = reinterpret_cast<const int4*>(P.elem_pos + (int64_t)cell * Meta::NPOS);
+#pragma unroll
+          for (int i = 0; i < NP16; ++i) rb.pos[i] = __ldg(src + i);
+        }
+      }
+      rc.t = td;
+      rc.valid = false;
+      if (td >= 0) {
+        const int64_t k0 = td * CB;
+        const int nent = (int)((P.num_entries - k0) < CB ? (P.num_entries - k0) : CB);
+        rc.nent = nent;
+        rc.valid = lane < nent;
+        const int64_t k = k0 + (rc.valid ? lane : nent - 1);
+        rc.o0 = __ldg(P.offsets + k);
+        rc.o1 = __ldg(P.offsets + k + 1);
+        rc.cell = __ldg(P.cells + k);
+      }
+      if (td >= 0) td = grab();
+    }
+  } else {
+    // =========================== consumer warps ===========================================
+    const int r = lane & (G - 1), grp = lane / G;
+    uint32_t ended = 0, parity = 0;
+    int s = 0;
+    while (ended != (1u << NPW) - 1u) {
+      if (!((ended >> s) & 1u)) {
+        mbar_wait(&full_bar[s], parity);
+        Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
+        const int nent = M.nent;
+        if (nent < 0) {
+          ended |= 1u << s;
+        } else {
+          for (;;) {
+            int e0 = 0;
+            if (lane == 0) e0 = atomicAdd(&M.next, CPW);
+            e0 = __shfl_sync(0xffffffffu, e0, 0);
+            if (e0 >= nent) break;
+            const bool active = e0 + grp < nent;
+            const int e = active ? M.order[e0 + grp] : 0;
+            if constexpr (MODE == 1) moment_process_entry<T, CB>(P, M, e, active);
+            else staged_process_entry<T, G, CB>(P, M, e, active, r, msum);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+      }
+      if (++s == NPW) {
+        s = 0;
+        parity ^= 1;
+      }
+    }
+  }
+  if constexpr (T::RANK == 0) block_sum_atomic(msum, P.out);
+}
+
+
+}  // namespace cq

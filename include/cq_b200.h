@@ -105,7 +105,13 @@ typedef struct cq_mesh {
   int64_t num_nodes;
   const int32_t* geom_dofmap;
   const double* coords;
+  /* Optional hints from cq_mesh_classify (0 = unknown, always safe):
+   *   CQ_MESH_AXIS_ALIGNED: every cell has a constant diagonal Jacobian (what create_rectangle /
+   *   create_box produce); enables the moment kernels for mass / stiffness on quadrilaterals. */
+  int32_t flags;
 } cq_mesh;
+
+#define CQ_MESH_AXIS_ALIGNED 1
 
 /* Function-space data as utils.get_dofs returns it (utils.py:33-63), kept un-expanded:
  *   dofmap [num_cells, n] int32, n = (degree+1)^gdim scalar dofs per cell; the blocked index
@@ -162,7 +168,8 @@ int cq_ctx_destroy(cq_ctx* ctx);
 int cq_ctx_check(cq_ctx* ctx, void* stream);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t cq_ctx_launch_count(const cq_ctx* ctx);
-/* Kernel variant: 0 = auto, 1 = direct-load kernel, 2 = bulk-copy (TMA) staged persistent kernel. */
+/* Kernel variant: 0 = auto, 1 = direct-load kernel only, 2 = bulk-copy (TMA) staged persistent
+ * kernel only (error when not applicable), 3 = like 0 but never the moment kernels. */
 int cq_ctx_set_variant(cq_ctx* ctx, int variant);
 
 /* ---- the hot path (device pointers) ---------------------------------------------------- */
@@ -176,6 +183,10 @@ int cq_assemble_vector(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
  * space may be NULL when the form has no coefficient. */
 int cq_assemble_scalar(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
                        const cq_space* space, const cq_quadrature* qr, double* m, void* stream);
+
+/* ---- mesh classification (setup, not the timed path) ------------------------------------------
+ * Sets *flags to the cq_mesh.flags bits that hold for every cell of the mesh. Synchronous. */
+int cq_mesh_classify(cq_ctx* ctx, int cell_type, const cq_mesh* mesh, int32_t* flags, void* stream);
 
 /* ---- scatter map (setup, not the timed path) -----------------------------------------------
  * out [num_cells, cq_scatter_map_stride()] uint8: out[c*stride + i*n + j] = position of column

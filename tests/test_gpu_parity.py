@@ -179,6 +179,32 @@ def test_input_conventions(cuda_backend, oracle_backend):
     assert close(A.data, oracle_backend.matrix(forms.mass(V), [(cells, P2, W2)]).data)
 
 
+@pytest.mark.parametrize("degree,bs", [(1, 1), (2, 1), (1, 2), (2, 2)])
+def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
+    """Axis-aligned quadrilateral meshes take the monomial-moment kernel for mass / stiffness
+    (cq_moment.cuh); the result must equal both the oracle and the point-by-point kernels."""
+    from customquad_b200.assemble import mesh_on_device, set_variant
+    import torch
+
+    mesh = cq.create_rectangle([[-1.11, -1.51], [1.55, 1.22]], [23, 17])
+    assert mesh_on_device(mesh, torch.device("cuda", torch.cuda.current_device()))[2] == 1  # CQ_MESH_AXIS_ALIGNED
+    V = cq.FunctionSpace(mesh, ("Lagrange", degree)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", degree))
+    rng = np.random.default_rng(31)
+    cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 40)])
+    qr = synthetic_ragged(cells, 2, 0, 70, seed=13)
+    for form in (forms.mass(V), forms.stiffness(V)):
+        R = oracle_backend.matrix(form, [qr])
+        set_variant(0)
+        A = cuda_backend.matrix(form, [qr])
+        set_variant(3)  # same staged kernel family without moments
+        B = cuda_backend.matrix(form, [qr])
+        set_variant(0)
+        assert close(A.data, R.data), f"{form.kind.name}: {np.max(np.abs(A.data - R.data)) / np.max(np.abs(R.data)):.3e}"
+        assert close(B.data, R.data)
+    dist = make_mesh(2, True)
+    assert mesh_on_device(dist, torch.device("cuda", torch.cuda.current_device()))[2] == 0
+
+
 def test_staged_kernel_stage_overflow_and_tails(cuda_backend, oracle_backend):
     """Staged kernel corner cases: a rule far longer than a shared-memory stage (read from global
     memory), an odd total point count (manual tail copy), many stages, zero-point entries."""
