@@ -98,19 +98,20 @@ def algorithmic_bytes(num_cells, num_points, gdim, nv, n, num_nodes, nnz):
     return num_cells * (4 + 8 + 4 * nv + 4 * n) + num_points * 8 * (gdim + 1) + 24 * num_nodes + 8 * nnz
 
 
-def build_problem(nx, ny, col0=0, total_nx=None):
-    """Mesh slab + spaces + synthetic ragged rule (SURVEY.md 8d generator, seed 20231)."""
+def build_problem(nx, ny, rank=0, world=1):
+    """Mesh (slab `rank` of a (nx*world) x ny mesh) + spaces + synthetic ragged rule for the cells
+    this rank assembles (SURVEY.md 8d generator, seed 20231 + rank)."""
     import customquad_b200 as cq
-    from customquad_b200 import forms
+    from customquad_b200 import dist as cqdist, forms
     from customquad_b200.quadrature import synthetic_ragged
 
-    total_nx = total_nx or nx
     hx = (XMAX[0] - XMIN[0]) / MESH_N
-    mesh = cq.create_rectangle([[XMIN[0] + col0 * hx, XMIN[1]], [XMIN[0] + (col0 + nx) * hx, XMAX[1]]], [nx, ny])
+    slab = cqdist.make_slab([[XMIN[0], XMIN[1]], [XMIN[0] + nx * world * hx, XMAX[1]]], [nx * world, ny], rank, world)
+    mesh = slab.mesh
     spaces = {1: cq.FunctionSpace(mesh, ("Lagrange", 1)), 2: cq.FunctionSpace(mesh, ("Lagrange", 2))}
     fl = [(name, getattr(forms, kind)(spaces[deg]), deg) for name, deg, kind in FORMS]
-    qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 2, NQ_LO, NQ_HI, seed=20231 + col0)
-    return mesh, spaces, fl, qr
+    qr = synthetic_ragged(slab.cells, 2, NQ_LO, NQ_HI, seed=20231 + rank)
+    return mesh, spaces, fl, qr, slab
 
 
 # ------------------------------------------------------------------------------------------------
@@ -125,7 +126,7 @@ def run_reference(args):
     oracle.build()
     threads = oracle.max_threads()
     sample_cols = 192  # 192 x 2048 = 393,216 cells per step and form (~9% of the workload)
-    mesh, spaces, fl, qr = build_problem(sample_cols, MESH_N)
+    mesh, spaces, fl, qr, _ = build_problem(sample_cols, MESH_N)
     pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
 
     def step():
@@ -168,7 +169,7 @@ def cpu_baseline_sample():
 
     threads = oracle.max_threads()
     cols = 512  # 512 x 2048 = 1,048,576 cells (a quarter of the workload), all 4 forms once
-    mesh, spaces, fl, qr = build_problem(cols, MESH_N)
+    mesh, spaces, fl, qr, _ = build_problem(cols, MESH_N)
     pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
     oracle.assemble_matrix(fl[0][1], [qr.select(np.arange(4096))], nthreads=threads, pattern=pats[1])  # warm up threads
     t0 = time.perf_counter()
@@ -199,14 +200,18 @@ def run_gpu(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
 
     log("building problem")
-    mesh, spaces, fl, qr = build_problem(MESH_N, MESH_N, col0=rank * MESH_N, total_nx=MESH_N * world)
+    mesh, spaces, fl, qr, slab = build_problem(MESH_N, MESH_N, rank, world)
     C_cells, P_pts = qr.num_entries, qr.num_points
     mats = {name: asm.create_matrix(form) for name, form, _ in fl}
     exch = None
     if world > 1:
         from customquad_b200 import dist as cqdist
 
-        exch = {name: cqdist.SlabExchange(spaces[deg], mats[name], rank, world) for name, _, deg in fl}
+        exch = {}
+        for name, _, deg in fl:
+            ex = cqdist.SlabExchange(spaces[deg], slab)
+            ex.set_pattern(mats[name].indptr, mats[name].indices)
+            exch[name] = ex
     asm.qr_on_device(qr, dev)  # inputs resident in HBM before the timed region
     ctx_launch0 = None
 
@@ -218,7 +223,7 @@ def run_gpu(args):
             A.data.zero_()  # A.zeroEntries() (assemble_matrix.py:20)
             asm.assemble_matrix(form, [qr], A=A)
             if exch is not None:
-                exch[name].exchange()
+                exch[name].exchange_matrix(A.data)
             if events is not None:
                 events[i][1].record()
 
@@ -298,7 +303,7 @@ def run_gpu(args):
             for name, form, _ in fl:
                 asm.assemble_matrix_host(form, hq_np, mats[name], vals[name])
                 if exch is not None:
-                    exch[name].exchange()
+                    exch[name].exchange_matrix(mats[name].data)
 
         log("e2e: warm-up")
         for _ in range(2):
