@@ -7,7 +7,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcq_b200.so")
+LIB_PATH = os.environ.get("CQ_LIB", os.path.join(HERE, "libcq_b200.so"))  # CQ_LIB: experiment builds
 
 CQ_OK = 0
 CQ_ERR_SPARSITY = -4

@@ -35,6 +35,7 @@ struct KParams {
   int64_t num_points;                    // length of pts / w (bulk-copy tail handling)
   int stage_points;                      // points capacity of one smem stage
   int mesh_flags;                        // cq_mesh.flags
+  int dbg;                               // profiling experiments only (CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)
   int elem_out;    // 1: write un-scattered element tensors to out[k, :]
   double betaN;

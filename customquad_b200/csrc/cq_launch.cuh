@@ -1,6 +1,8 @@
 // cq_launch.cuh -- launch helpers shared by the cq_launch_*.cu translation units: the direct
 // (grid-strided) kernel and the bulk-copy staged persistent kernel, and the choice between them.
 #pragma once
+#include <cstdlib>
+
 #include "cq_internal.h"
 #include "cq_staged_kernel.cuh"
 
@@ -38,11 +40,14 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
   if (budget / NPW <= fixed + 64 * per_point) { set_error("staged kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
   const int64_t pb_max = (int64_t)((budget / NPW - fixed) / per_point) & ~(int64_t)1;
-  int64_t pb = (P.num_points / (P.num_entries > 0 ? P.num_entries : 1) + 1) * CB * 5 / 4 + 64;
+  static const double factor = getenv("CQ_STAGE_FACTOR") ? atof(getenv("CQ_STAGE_FACTOR")) : 1.25;  // stage capacity / mean stage size
+  int64_t pb = (int64_t)((P.num_points / (P.num_entries > 0 ? P.num_entries : 1) + 1) * CB * factor) + 64;
   pb = (pb + 1) & ~(int64_t)1;
   if (pb > pb_max) pb = pb_max;
   if (pb < 64) pb = 64;
   P.stage_points = (int)pb;
+  static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
+  P.dbg = dbg;
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
   static thread_local size_t configured = 0;  // per kernel instantiation
   if (smem > configured) {
@@ -65,6 +70,12 @@ struct StagedShape {
   static constexpr int G = T::NACC <= 16 ? 4 : 8;
 };
 
+#ifndef CQ_MOMENT_G
+#define CQ_MOMENT_G 2
+#endif
+#ifndef CQ_MOMENT_NPW
+#define CQ_MOMENT_NPW 4
+#endif
 // mesh flags (cq_mesh.flags)
 constexpr int MESH_AXIS_ALIGNED = 1;
 
@@ -74,7 +85,7 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
   if (staged_ok<T>(ctx, P)) {
     // mass / stiffness on quadrilaterals whose Jacobian is constant and diagonal: moment kernel
     if constexpr (T::DIM == 2 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {
-      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) return launch_staged<T, 1, 4, 4, 1>(ctx, P, s);
+      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
     }
     return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
   }

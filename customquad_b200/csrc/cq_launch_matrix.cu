@@ -19,6 +19,10 @@ static int launch_matrix_form(cq_ctx* ctx, const cq_form_desc& f, const KParams&
   if (quad && f.degree == 1) return launch_auto<FormTraits<FORM, 2, 1, 1, CQ_FN_CONST>>(ctx, P, s);
   if (quad && f.degree == 2) return launch_auto<FormTraits<FORM, 2, 2, 1, CQ_FN_CONST>>(ctx, P, s);
   if (!quad && f.degree == 1) return launch_auto<FormTraits<FORM, 3, 1, 1, CQ_FN_CONST>>(ctx, P, s);
+  // Q2 hexahedron: FP64 tensor-core contraction, staged (warp per entry) when the scatter map is there
+  using TQ2 = FormTraits<FORM, 3, 2, 1, CQ_FN_CONST>;
+  if (staged_ok<TQ2>(ctx, P)) return launch_staged<TQ2, 32, TQ2::NEED_NORMAL ? 2 : 3, 5, 2>(ctx, P, s);
+  if (ctx->variant == 2) { set_error("staged kernel requested but not applicable"); return CQ_ERR_UNSUPPORTED; }
   return launch_dmma<FORM>(ctx, P, s);
 }
 

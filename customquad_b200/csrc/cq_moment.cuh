@@ -74,23 +74,47 @@ CQ_HD constexpr int quad_dof_of(int a0, int a1) {
   return -1;
 }
 
+// Per-entry scatter data held in registers: the scatter positions (one byte each, packed) and the
+// CSR row starts -- loaded from the stage header once per entry instead of once per value.
 template <class T, int CB>
-CQ_DEVINL void scatter_value(const KParams& P, const StageMeta<T, CB>& M, const int e, const int i, const int j, const double v) {
-  constexpr int N = T::N;
-  const int pij = M.pos[e][i * N + j];
-  const long long si = M.rowstart[i][e];
-  const int bs = P.bs;
-  if (bs == 1) {
-    red_add_f64(P.values + si + pij, v);
-  } else {
-    const int li = M.rowlen[i][e];
-    for (int a = 0; a < bs; ++a) red_add_f64(P.values + si + (long long)a * li + pij * bs + a, v);
+struct ScatterRegs {
+  static constexpr int N = T::N;
+  static constexpr int NW = StageMeta<T, CB>::NPOS / 4;
+  uint32_t posw[NW];
+  long long rs[N];
+  int rl[N];
+  CQ_DEVINL void load(const KParams& P, const StageMeta<T, CB>& M, const int e) {
+    const int4* src = reinterpret_cast<const int4*>(&M.pos[e][0]);
+#pragma unroll
+    for (int i = 0; i < NW / 4; ++i) {
+      const int4 v = src[i];
+      posw[4 * i] = v.x; posw[4 * i + 1] = v.y; posw[4 * i + 2] = v.z; posw[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      rs[i] = M.rowstart[i][e];
+      rl[i] = P.bs == 1 ? 0 : M.rowlen[i][e];
+    }
   }
-}
+  template <int I, int J>
+  CQ_DEVINL void add(const KParams& P, const double v) const {
+    constexpr int k = I * N + J;
+    const int pij = (posw[k >> 2] >> (8 * (k & 3))) & 0xff;
+    const int bs = P.bs;
+    if (bs == 1) {
+      red_add_f64(P.values + rs[I] + pij, v);
+    } else {
+      for (int a = 0; a < bs; ++a) red_add_f64(P.values + rs[I] + (long long)a * rl[I] + pij * bs + a, v);
+    }
+  }
+};
 
-// T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}
-template <class T, int CB>
-CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active) {
+// T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}.  G lanes per entry: lane r takes the
+// points r, r+G, ...; the moments are all-reduced over the group; every lane expands all values
+// (cheap FP64 work) but scatters only the values k = i*n+j with k % G == r, so the expensive part
+// -- the REDs -- is split, not duplicated.
+template <class T, int G, int CB>
+CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active, const int r) {
   constexpr int DEG = T::DEG;
   using Q = Poly1D<DEG>;
   constexpr int Pn = Q::P;
@@ -104,7 +128,7 @@ CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M,
   const double* pp = M.pts[e];
   const double* wp = M.w[e];
 #pragma unroll 2
-  for (int q = 0; q < nq; ++q) {
+  for (int q = r; q < nq; q += G) {
     const double2 xy = *reinterpret_cast<const double2*>(pp + 2 * q);
     const double w = wp[q];
     const double tx = xy.x - 0.5, ty = xy.y - 0.5;
@@ -123,7 +147,17 @@ CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M,
 #pragma unroll
       for (int q2 = 0; q2 < Pn; ++q2) mu[p][q2] = fma(X[p], WY[q2], mu[p][q2]);
   }
-  if (!active) return;
+  if constexpr (G > 1) {
+#pragma unroll
+    for (int st = G / 2; st >= 1; st >>= 1)
+#pragma unroll
+      for (int p = 0; p < Pn; ++p)
+#pragma unroll
+        for (int q = 0; q < Pn; ++q) mu[p][q] += __shfl_xor_sync(0xffffffffu, mu[p][q], st);
+  }
+  if (!active || P.dbg == 2) return;
+  ScatterRegs<T, CB> S;
+  S.load(P, M, e);
   // per-cell constants: J = diag(J00, J11) (axis-aligned cell; checked for the whole mesh at setup)
   const double J00 = M.X[2 * 2 + 0][e] - M.X[0][e];  // local vertex 2 is the +x neighbour (Lattice<2,1>)
   const double J11 = M.X[1 * 2 + 1][e] - M.X[1][e];  // local vertex 1 is the +y neighbour
@@ -166,10 +200,10 @@ CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M,
           });
           const double v = STIFF ? fma(k0, m0, k1 * m1) : k0 * m0;
           constexpr int i = quad_dof_of<DEG>(a0, a1), j = quad_dof_of<DEG>(c0, c1);
-          scatter_value<T, CB>(P, M, e, i, j, v);
+          if (G == 1 || (i * T::N + j) % G == r) S.template add<i, j>(P, v);
           if constexpr (a0 != c0) {  // x-swapped entry has the same value (the x rows are symmetric)
             constexpr int i2 = quad_dof_of<DEG>(c0, a1), j2 = quad_dof_of<DEG>(a0, c1);
-            scatter_value<T, CB>(P, M, e, i2, j2, v);
+            if (G == 1 || (i2 * T::N + j2) % G == r) S.template add<i2, j2>(P, v);
           }
         });
       });

@@ -1,5 +1,6 @@
 // cq_staged_kernel.cuh -- the staged persistent kernel (producer / consumer roles); see cq_staged.cuh
 #pragma once
+#include "cq_dmma.cuh"
 #include "cq_moment.cuh"
 #include "cq_staged.cuh"
 
@@ -7,7 +8,8 @@ namespace cq {
 
 // ---- the kernel ------------------------------------------------------------------------------------------
 // MODE 0: G lanes per entry accumulate the element tensor point by point (any form, any cell).
-// MODE 1: one thread per entry, monomial moments (cq_moment.cuh; G must be 1).
+// MODE 1: G lanes per entry, monomial moments (cq_moment.cuh).
+// MODE 2: one warp per entry, FP64 tensor-core contraction for the Q2 hexahedron (cq_dmma.cuh; G = 32).
 template <class T, int G, int NPW, int NCW, int MODE>
 __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(const KParams P) {
   constexpr int CB = 32;
@@ -47,7 +49,8 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
     double* s_pts = reinterpret_cast<double*>(base + Lay::meta_bytes);
     double* s_w = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB));
     double* s_nrm = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB) + Lay::w_bytes(PB));
-    constexpr int NP16 = Meta::MAT ? Meta::NPOS / 16 : 1;
+    constexpr bool POS_BULK = Meta::MAT && Meta::NPOS > 128;  // large rows: bulk copy instead of registers
+    constexpr int NP16 = (Meta::MAT && !POS_BULK) ? Meta::NPOS / 16 : 1;
     struct Regs {
       long long t;  // stage index; -2: pipeline bubble, -1: no more work
       int nent;
@@ -64,13 +67,10 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
     Regs ra, rb, rc;
     ra.t = rb.t = rc.t = -2;
     ra.valid = rb.valid = rc.valid = false;
-    auto grab = [&]() -> long long {
-      long long t = 0;
-      if (lane == 0) t = atomicAdd(P.work_counter, 1u);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      return t < num_stages ? t : -1;
-    };
-    long long td = grab();
+    // the work counter is read one iteration ahead: lane 0 keeps the raw ticket, the broadcast
+    // (which has to wait for the atomic's round trip) happens at the next advance
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(P.work_counter, 1u);
     uint32_t parity = 0;
     bool first = true;
     for (;;) {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         if (Pa + cnt_copy > P.num_points) { cnt_copy = cnt - 1; tail = 1; }
         if (lane == 0) {
           const uint32_t b_pts = (uint32_t)(cnt_copy * DIM * 8), b_w = (uint32_t)(cnt_copy * 8);
-          mbar_arrive_expect_tx(&full_bar[warp], b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w);
+          mbar_arrive_expect_tx(&full_bar[warp], b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w + (POS_BULK ? (uint32_t)(nent * Meta::NPOS) : 0u));
           if (cnt_copy > 0) {
             bulk_g2s(s_pts, P.pts + Pa * DIM, b_pts, &full_bar[warp]);
             bulk_g2s(s_w, P.w + Pa, b_w, &full_bar[warp]);
@@ -126,10 +126,13 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         M.w[lane] = staged ? s_w + (o0 - Pa) : P.w + o0;
         if constexpr (T::NEED_NORMAL) M.nrm[lane] = staged ? s_nrm + (o0 - Pa) * DIM : P.normals + o0 * DIM;
         if (ra.valid) {
+          if constexpr (POS_BULK) bulk_g2s(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, &full_bar[warp]);
           if constexpr (Meta::MAT) {
-            int4* dst = reinterpret_cast<int4*>(&M.pos[lane][0]);
+            if constexpr (!POS_BULK) {
+              int4* dst = reinterpret_cast<int4*>(&M.pos[lane][0]);
 #pragma unroll
-            for (int i = 0; i < NP16; ++i) dst[i] = ra.pos[i];
+              for (int i = 0; i < NP16; ++i) dst[i] = ra.pos[i];
+            }
 #pragma unroll
             for (int i = 0; i < N; ++i) {
               M.rowstart[i][lane] = ra.rs[i];
@@ -201,12 +204,15 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
 #pragma unroll
           for (int i = 0; i < N; ++i) rb.dof[i] = __ldg(P.dofmap + (int64_t)cell * N + i);
         }
-        if constexpr (Meta::MAT) {
+        if constexpr (Meta::MAT && !POS_BULK) {
           const int4* src = reinterpret_cast<const int4*>(P.elem_pos + (int64_t)cell * Meta::NPOS);
 #pragma unroll
           for (int i = 0; i < NP16; ++i) rb.pos[i] = __ldg(src + i);
         }
       }
+      long long td = __shfl_sync(0xffffffffu, (long long)ticket, 0);
+      if (td >= num_stages) td = -1;
+      if (td >= 0 && lane == 0) ticket = atomicAdd(P.work_counter, 1u);
       rc.t = td;
       rc.valid = false;
       if (td >= 0) {
@@ -219,7 +225,6 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         rc.o1 = __ldg(P.offsets + k + 1);
         rc.cell = __ldg(P.cells + k);
       }
-      if (td >= 0) td = grab();
     }
   } else {
     // =========================== consumer warps ===========================================
@@ -234,14 +239,15 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         if (nent < 0) {
           ended |= 1u << s;
         } else {
-          for (;;) {
+          for (; P.dbg != 1;) {
             int e0 = 0;
             if (lane == 0) e0 = atomicAdd(&M.next, CPW);
             e0 = __shfl_sync(0xffffffffu, e0, 0);
             if (e0 >= nent) break;
             const bool active = e0 + grp < nent;
             const int e = active ? M.order[e0 + grp] : 0;
-            if constexpr (MODE == 1) moment_process_entry<T, CB>(P, M, e, active);
+            if constexpr (MODE == 2) dmma_process_entry<T, CB>(P, M, e);
+            else if constexpr (MODE == 1) moment_process_entry<T, G, CB>(P, M, e, active, r);
             else staged_process_entry<T, G, CB>(P, M, e, active, r, msum);
           }
           __syncwarp();
