@@ -62,6 +62,38 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
 }
 
+template <class T, int G, int NPW, int NMW, int NXW>
+static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
+  constexpr int CB = 32;
+  using Lay = StagedLayout<T, CB>;
+  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW>;
+  const size_t budget = (size_t)ctx->max_smem_optin - 1024;
+  const size_t per_point = (size_t)T::DIM * 8 + 8;
+  const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
+  if (budget / NPW <= fixed + 64 * per_point) { set_error("moment kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
+  const int64_t pb_max = (int64_t)((budget / NPW - fixed) / per_point) & ~(int64_t)1;
+  static const double factor = getenv("CQ_STAGE_FACTOR") ? atof(getenv("CQ_STAGE_FACTOR")) : 1.25;
+  int64_t pb = (int64_t)((P.num_points / (P.num_entries > 0 ? P.num_entries : 1) + 1) * CB * factor) + 64;
+  pb = (pb + 1) & ~(int64_t)1;
+  if (pb > pb_max) pb = pb_max;
+  if (pb < 64) pb = 64;
+  P.stage_points = (int)pb;
+  static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
+  P.dbg = dbg;
+  const size_t smem = NPW * Lay::stage_bytes((int)pb);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
+    configured = smem;
+  }
+  if (int rc = check_cuda(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s), "work_counter reset")) return rc;
+  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
+  const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
+  kernel<<<grid, (NPW + NMW + NXW) * 32, smem, s>>>(P);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "assemble_moment_split_kernel launch");
+}
+
 // consumer warps by accumulator size: the register file holds (NPW + NCW) * 32 threads
 template <class T>
 struct StagedShape {
@@ -85,7 +117,13 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
   if (staged_ok<T>(ctx, P)) {
     // mass / stiffness on quadrilaterals whose Jacobian is constant and diagonal: moment kernel
     if constexpr (T::DIM == 2 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {
-      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
+      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) {
+        // three-role kernel for Q1 (measured 1.00 vs 1.06 ms on the bench workload); for Q2 both
+        // organisations are bound by the L2 atomic rate of the 81 REDs per cell (2.56 vs 2.59 ms)
+        static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : (T::DEG == 1 ? 1 : 0);
+        if (split) return launch_moment_split<T, 4, 4, 8, T::DEG == 1 ? 2 : 3>(ctx, P, s);
+        return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
+      }
     }
     return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
   }

@@ -74,52 +74,62 @@ CQ_HD constexpr int quad_dof_of(int a0, int a1) {
   return -1;
 }
 
-// Per-entry scatter data held in registers: the scatter positions (one byte each, packed) and the
-// CSR row starts -- loaded from the stage header once per entry instead of once per value.
-template <class T, int CB>
+// Per-entry scatter data held in registers: the scatter positions (one byte each, packed) and one
+// pointer per local row (values + CSR row start of component `comp`), computed once per entry, so
+// that a value costs: byte extract, one 64-bit multiply-add, one RED.
+//   UNIT (bs == 1): slot = rowstart[i] + pos
+//   blocked:        slot = rowstart[i] + comp*rowlen[i] + pos*bs + comp   (stride = bs)
+template <class T, int CB, bool UNIT>
 struct ScatterRegs {
   static constexpr int N = T::N;
   static constexpr int NW = StageMeta<T, CB>::NPOS / 4;
   uint32_t posw[NW];
-  long long rs[N];
-  int rl[N];
-  CQ_DEVINL void load(const KParams& P, const StageMeta<T, CB>& M, const int e) {
+  double* rowp[N];
+  int stride;
+  CQ_DEVINL void load(const KParams& P, const StageMeta<T, CB>& M, const int e, const int comp) {
     const int4* src = reinterpret_cast<const int4*>(&M.pos[e][0]);
 #pragma unroll
     for (int i = 0; i < NW / 4; ++i) {
       const int4 v = src[i];
       posw[4 * i] = v.x; posw[4 * i + 1] = v.y; posw[4 * i + 2] = v.z; posw[4 * i + 3] = v.w;
     }
+    stride = UNIT ? 1 : P.bs;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      rs[i] = M.rowstart[i][e];
-      rl[i] = P.bs == 1 ? 0 : M.rowlen[i][e];
+      if constexpr (UNIT) rowp[i] = P.values + M.rowstart[i][e];
+      else rowp[i] = P.values + M.rowstart[i][e] + (long long)comp * M.rowlen[i][e] + comp;
     }
   }
   template <int I, int J>
-  CQ_DEVINL void add(const KParams& P, const double v) const {
+  CQ_DEVINL void add(const double v) const {
     constexpr int k = I * N + J;
-    const int pij = (posw[k >> 2] >> (8 * (k & 3))) & 0xff;
-    const int bs = P.bs;
-    if (bs == 1) {
-      red_add_f64(P.values + rs[I] + pij, v);
-    } else {
-      for (int a = 0; a < bs; ++a) red_add_f64(P.values + rs[I] + (long long)a * rl[I] + pij * bs + a, v);
-    }
+    const unsigned pij = (posw[k >> 2] >> (8 * (k & 3))) & 0xffu;
+    if constexpr (UNIT) red_add_f64(rowp[I] + pij, v);
+    else red_add_f64(rowp[I] + pij * (unsigned)stride, v);
   }
 };
 
-// T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}.  G lanes per entry: lane r takes the
-// points r, r+G, ...; the moments are all-reduced over the group; every lane expands all values
-// (cheap FP64 work) but scatters only the values k = i*n+j with k % G == r, so the expensive part
-// -- the REDs -- is split, not duplicated.
+// owner (expansion warp) of the unordered x-pair number idx when the expansion is split over NXW warps
+template <int DEG, int NXW>
+CQ_HD constexpr int pair_owner(int idx) {
+  if (NXW == 1) return 0;
+  if (DEG == 1) {  // pairs (0,0) (0,1) (1,1): 4 + 8 + 4 values
+    constexpr int o2[3] = {1, 0, 1};
+    return NXW == 2 ? o2[idx] : idx % NXW;
+  }
+  // pairs (0,0) (0,1) (0,2) (1,1) (1,2) (2,2): 9 18 18 9 18 9 values
+  constexpr int o3[6] = {2, 0, 1, 1, 2, 0};
+  constexpr int o2[6] = {0, 0, 1, 1, 0, 1};  // 9+18+18 = 45 | 18+9+9 = 36
+  return NXW == 3 ? o3[idx] : (NXW == 2 ? o2[idx] : idx % NXW);
+}
+
+// T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}.
+// Point loop: G lanes per entry, lane r takes the points r, r+G, ...; the moments are all-reduced over
+// the group (every lane ends with the full set).
 template <class T, int G, int CB>
-CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active, const int r) {
-  constexpr int DEG = T::DEG;
-  using Q = Poly1D<DEG>;
-  constexpr int Pn = Q::P;
-  constexpr bool STIFF = T::FORM_ID == CQ_FORM_STIFFNESS;
-  double mu[Pn][Pn];
+CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const bool active, const int r,
+                                 double (&mu)[2 * T::DEG + 1][2 * T::DEG + 1]) {
+  constexpr int Pn = 2 * T::DEG + 1;
 #pragma unroll
   for (int p = 0; p < Pn; ++p)
 #pragma unroll
@@ -155,9 +165,20 @@ CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M,
 #pragma unroll
         for (int q = 0; q < Pn; ++q) mu[p][q] += __shfl_xor_sync(0xffffffffu, mu[p][q], st);
   }
-  if (!active || P.dbg == 2) return;
-  ScatterRegs<T, CB> S;
-  S.load(P, M, e);
+}
+
+// Expansion moments -> element tensor values, each scattered as soon as it is formed.
+//   XW / NXW: this caller expands only the x-pairs owned by expansion warp XW (NXW == 1: all of them)
+//   G, r:     with NXW == 1 and G lanes holding the same moments, lane r scatters the values k % G == r
+template <class T, int G, int CB, int XW, int NXW, bool UNIT>
+CQ_DEVINL void moment_expand_comp(const KParams& P, const StageMeta<T, CB>& M, const int e, const int r, const int comp,
+                                  const double (&mu)[2 * T::DEG + 1][2 * T::DEG + 1]) {
+  constexpr int DEG = T::DEG;
+  using Q = Poly1D<DEG>;
+  constexpr int Pn = Q::P;
+  constexpr bool STIFF = T::FORM_ID == CQ_FORM_STIFFNESS;
+  ScatterRegs<T, CB, UNIT> S;
+  S.load(P, M, e, comp);
   // per-cell constants: J = diag(J00, J11) (axis-aligned cell; checked for the whole mesh at setup)
   const double J00 = M.X[2 * 2 + 0][e] - M.X[0][e];  // local vertex 2 is the +x neighbour (Lattice<2,1>)
   const double J11 = M.X[1 * 2 + 1][e] - M.X[1][e];  // local vertex 1 is the +y neighbour
@@ -168,47 +189,71 @@ CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M,
   static_for<0, DEG + 1>([&](auto A0) {
     static_for<decltype(A0)::value, DEG + 1>([&](auto C0) {
       constexpr int a0 = decltype(A0)::value, c0 = decltype(C0)::value;
-      // contract the x index:  U0[q] = sum_p R00x[p] mu[p][q],  U1[q] = sum_p R11x[p] mu[p][q]
-      double U0[Pn], U1[Pn];
+      constexpr int pair_idx = a0 * (DEG + 1) - a0 * (a0 - 1) / 2 + (c0 - a0);
+      if constexpr (pair_owner<DEG, NXW>(pair_idx) == XW) {
+        // contract the x index:  U0[q] = sum_p R00x[p] mu[p][q],  U1[q] = sum_p R11x[p] mu[p][q]
+        double U0[Pn], U1[Pn];
 #pragma unroll
-      for (int q = 0; q < Pn; ++q) U0[q] = U1[q] = 0.0;
-      static_for<0, Pn>([&](auto PP) {
-        constexpr int p = decltype(PP)::value;
-        constexpr double r00 = Q::R00(a0, c0, p), r11 = Q::R11(a0, c0, p);
-        if constexpr (r00 != 0.0) {
+        for (int q = 0; q < Pn; ++q) U0[q] = U1[q] = 0.0;
+        static_for<0, Pn>([&](auto PP) {
+          constexpr int p = decltype(PP)::value;
+          constexpr double r00 = Q::R00(a0, c0, p), r11 = Q::R11(a0, c0, p);
+          if constexpr (r00 != 0.0) {
 #pragma unroll
-          for (int q = 0; q < Pn; ++q) U0[q] = fma(r00, mu[p][q], U0[q]);
-        }
-        if constexpr (STIFF && r11 != 0.0) {
+            for (int q = 0; q < Pn; ++q) U0[q] = fma(r00, mu[p][q], U0[q]);
+          }
+          if constexpr (STIFF && r11 != 0.0) {
 #pragma unroll
-          for (int q = 0; q < Pn; ++q) U1[q] = fma(r11, mu[p][q], U1[q]);
-        }
-      });
-      static_for<0, DEG + 1>([&](auto A1) {
-        static_for<0, DEG + 1>([&](auto C1) {
-          constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
-          double m0 = 0.0, m1 = 0.0;  // y contractions
-          static_for<0, Pn>([&](auto QQ) {
-            constexpr int q = decltype(QQ)::value;
-            constexpr double r00 = Q::R00(a1, c1, q), r11 = Q::R11(a1, c1, q);
-            if constexpr (STIFF) {
-              if constexpr (r00 != 0.0) m0 = fma(r00, U1[q], m0);  // d/dx d/dx: R11 in x, R00 in y
-              if constexpr (r11 != 0.0) m1 = fma(r11, U0[q], m1);  // d/dy d/dy: R00 in x, R11 in y
-            } else {
-              if constexpr (r00 != 0.0) m0 = fma(r00, U0[q], m0);
-            }
-          });
-          const double v = STIFF ? fma(k0, m0, k1 * m1) : k0 * m0;
-          constexpr int i = quad_dof_of<DEG>(a0, a1), j = quad_dof_of<DEG>(c0, c1);
-          if (G == 1 || (i * T::N + j) % G == r) S.template add<i, j>(P, v);
-          if constexpr (a0 != c0) {  // x-swapped entry has the same value (the x rows are symmetric)
-            constexpr int i2 = quad_dof_of<DEG>(c0, a1), j2 = quad_dof_of<DEG>(a0, c1);
-            if (G == 1 || (i2 * T::N + j2) % G == r) S.template add<i2, j2>(P, v);
+            for (int q = 0; q < Pn; ++q) U1[q] = fma(r11, mu[p][q], U1[q]);
           }
         });
-      });
+        static_for<0, DEG + 1>([&](auto A1) {
+          static_for<0, DEG + 1>([&](auto C1) {
+            constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
+            double m0 = 0.0, m1 = 0.0;  // y contractions
+            static_for<0, Pn>([&](auto QQ) {
+              constexpr int q = decltype(QQ)::value;
+              constexpr double r00 = Q::R00(a1, c1, q), r11 = Q::R11(a1, c1, q);
+              if constexpr (STIFF) {
+                if constexpr (r00 != 0.0) m0 = fma(r00, U1[q], m0);  // d/dx d/dx: R11 in x, R00 in y
+                if constexpr (r11 != 0.0) m1 = fma(r11, U0[q], m1);  // d/dy d/dy: R00 in x, R11 in y
+              } else {
+                if constexpr (r00 != 0.0) m0 = fma(r00, U0[q], m0);
+              }
+            });
+            const double v = STIFF ? fma(k0, m0, k1 * m1) : k0 * m0;
+            constexpr int i = quad_dof_of<DEG>(a0, a1), j = quad_dof_of<DEG>(c0, c1);
+            if (G == 1 || NXW > 1 || (i * T::N + j) % G == r) S.template add<i, j>(v);
+            if constexpr (a0 != c0) {  // x-swapped entry has the same value (the x rows are symmetric)
+              constexpr int i2 = quad_dof_of<DEG>(c0, a1), j2 = quad_dof_of<DEG>(a0, c1);
+              if (G == 1 || NXW > 1 || (i2 * T::N + j2) % G == r) S.template add<i2, j2>(v);
+            }
+          });
+        });
+      }
     });
   });
+}
+
+// bs == 1: unit-stride scatter; blocked spaces: the scalar block is scattered once per component
+template <class T, int G, int CB, int XW, int NXW>
+CQ_DEVINL void moment_expand(const KParams& P, const StageMeta<T, CB>& M, const int e, const int r,
+                             const double (&mu)[2 * T::DEG + 1][2 * T::DEG + 1]) {
+  if (P.bs == 1) {
+    moment_expand_comp<T, G, CB, XW, NXW, true>(P, M, e, r, 0, mu);
+  } else {
+#pragma unroll 1
+    for (int comp = 0; comp < P.bs; ++comp) moment_expand_comp<T, G, CB, XW, NXW, false>(P, M, e, r, comp, mu);
+  }
+}
+
+// MODE 1 of the staged kernel: the same warp does the point loop and the expansion
+template <class T, int G, int CB>
+CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active, const int r) {
+  double mu[2 * T::DEG + 1][2 * T::DEG + 1];
+  moment_accumulate<T, G, CB>(M, e, active, r, mu);
+  if (!active || P.dbg == 2) return;
+  moment_expand<T, G, CB, 0, 1>(P, M, e, r, mu);
 }
 
 }  // namespace cq

@@ -78,6 +78,10 @@ struct StageMeta {
   int dofs[VEC ? N : 1][CB];
   alignas(16) uint8_t pos[MAT ? CB : 1][MAT ? NPOS : 16];
   double coef[T::NEED_COEF ? T::NCOEF : 1][CB];
+  // monomial moments handed from the moment warps to the expansion warps (cq_moment.cuh, split kernel)
+  static constexpr bool MOM = T::DIM == 2 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS);
+  static constexpr int NMOM = MOM ? (2 * T::DEG + 1) * (2 * T::DEG + 1) : 1;
+  double mu[NMOM][CB];
 };
 
 template <class T, int CB>
@@ -91,9 +95,27 @@ struct StagedLayout {
 };
 
 // ---- consumer: one entry per group of G lanes --------------------------------------------------------
+// (i, j) of the accumulator slices a lane owns after the transpose-reduce: fixed for the whole kernel
+template <class T, int G>
+struct LaneEntries {
+  static constexpr int B = round_up(T::NACC, G) / G;
+  unsigned char i[B], j[B];
+  CQ_DEVINL void init(const int r) {
+#pragma unroll
+    for (int kk = 0; kk < B; ++kk) {
+      int ii = 0, jj = 0;
+      if constexpr (T::RANK == 2) {
+        if (r * B + kk < T::NACC) tri_unpack<T::N>(r * B + kk, ii, jj);
+      }
+      i[kk] = (unsigned char)ii;
+      j[kk] = (unsigned char)jj;
+    }
+  }
+};
+
 template <class T, int G, int CB>
 CQ_DEVINL void staged_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active, const int r,
-                                    double& msum) {
+                                    double& msum, const LaneEntries<T, G>& LE) {
   constexpr int DIM = T::DIM, N = T::N, NV = T::NV;
   constexpr int MPAD = round_up(T::NACC, G);
   double acc[MPAD];
@@ -153,19 +175,20 @@ CQ_DEVINL void staged_process_entry(const KParams& P, const StageMeta<T, CB>& M,
         for (int kk = 0; kk < B; ++kk) {
           const int en = r * B + kk;
           if (en < T::NACC) {
-            int i, j;
-            tri_unpack<N>(en, i, j);
+            const int i = LE.i[kk], j = LE.j[kk];
             const double v = acc[kk];
-            const int pij = M.pos[e][i * N + j], pji = M.pos[e][j * N + i];
-            const long long si = M.rowstart[i][e], sj = M.rowstart[j][e];
+            const unsigned pij = M.pos[e][i * N + j], pji = M.pos[e][j * N + i];
+            double* pi = P.values + M.rowstart[i][e];
+            double* pj = P.values + M.rowstart[j][e];
             if (bs == 1) {
-              red_add_f64(P.values + si + pij, v);
-              if (i != j) red_add_f64(P.values + sj + pji, v);
+              red_add_f64(pi + pij, v);
+              if (i != j) red_add_f64(pj + pji, v);
             } else {
               const int li = M.rowlen[i][e], lj = M.rowlen[j][e];
+#pragma unroll 1
               for (int a = 0; a < bs; ++a) {
-                red_add_f64(P.values + si + (long long)a * li + pij * bs + a, v);
-                if (i != j) red_add_f64(P.values + sj + (long long)a * lj + pji * bs + a, v);
+                red_add_f64(pi + (long long)a * li + pij * bs + a, v);
+                if (i != j) red_add_f64(pj + (long long)a * lj + pji * bs + a, v);
               }
             }
           }

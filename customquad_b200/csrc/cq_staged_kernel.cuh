@@ -6,45 +6,20 @@
 
 namespace cq {
 
-// ---- the kernel ------------------------------------------------------------------------------------------
-// MODE 0: G lanes per entry accumulate the element tensor point by point (any form, any cell).
-// MODE 1: G lanes per entry, monomial moments (cq_moment.cuh).
-// MODE 2: one warp per entry, FP64 tensor-core contraction for the Q2 hexahedron (cq_dmma.cuh; G = 32).
-template <class T, int G, int NPW, int NCW, int MODE>
-__global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(const KParams P) {
-  constexpr int CB = 32;
+// ---- producer role (one warp per stage slot) ----------------------------------------------------------
+template <class T, int G, int CB>
+CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* full_bar_w, uint64_t* empty_bar_w, const int lane,
+                               const int PB, const int64_t num_stages) {
   constexpr int DIM = T::DIM, N = T::N, NV = T::NV;
   using Meta = StageMeta<T, CB>;
   using Lay = StagedLayout<T, CB>;
-  constexpr int CPW = 32 / G;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t full_bar[NPW], empty_bar[NPW];
-  const int PB = P.stage_points;
-  const size_t stage_bytes = Lay::stage_bytes(PB);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < NPW; ++s) {
-      mbar_init(&full_bar[s], 2);     // producer lane 0 twice: expect_tx at copy issue, arrive after the header
-      mbar_init(&empty_bar[s], NCW);  // one elected lane per consumer warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
-  double msum = 0.0;
-
-  if (warp < NPW) {
+  {
     // =========================== producer warp: owns stage `warp` ===========================
     // Filling a stage is a chain of dependent global loads (work counter -> offsets, cell ids ->
     // dofmap rows -> vertex coordinates, CSR row starts): ~4 round trips.  The chain is software-
     // pipelined over three stages held in registers -- while stage A is being published, level 3
     // of stage B, level 2 of stage C and level 1 of stage D are in flight -- so a free slot only
     // waits for its bulk copy.
-    unsigned char* base = smem_raw + (size_t)warp * stage_bytes;
     Meta& M = *reinterpret_cast<Meta*>(base);
     double* s_pts = reinterpret_cast<double*>(base + Lay::meta_bytes);
     double* s_w = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB));
@@ -76,17 +51,17 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
     for (;;) {
       // ---------------- publish stage A ----------------
       if (ra.t == -1) {
-        if (!first) mbar_wait(&empty_bar[warp], parity);
+        if (!first) mbar_wait(empty_bar_w, parity);
         if (lane == 0) {
           M.nent = -1;
-          mbar_arrive(&full_bar[warp]);
-          mbar_arrive(&full_bar[warp]);
+          mbar_arrive(full_bar_w);
+          mbar_arrive(full_bar_w);
         }
         break;
       }
       if (ra.t >= 0) {
         if (!first) {
-          mbar_wait(&empty_bar[warp], parity);
+          mbar_wait(empty_bar_w, parity);
           parity ^= 1;
         }
         first = false;
@@ -102,11 +77,11 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         if (Pa + cnt_copy > P.num_points) { cnt_copy = cnt - 1; tail = 1; }
         if (lane == 0) {
           const uint32_t b_pts = (uint32_t)(cnt_copy * DIM * 8), b_w = (uint32_t)(cnt_copy * 8);
-          mbar_arrive_expect_tx(&full_bar[warp], b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w + (POS_BULK ? (uint32_t)(nent * Meta::NPOS) : 0u));
+          mbar_arrive_expect_tx(full_bar_w, b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w + (POS_BULK ? (uint32_t)(nent * Meta::NPOS) : 0u));
           if (cnt_copy > 0) {
-            bulk_g2s(s_pts, P.pts + Pa * DIM, b_pts, &full_bar[warp]);
-            bulk_g2s(s_w, P.w + Pa, b_w, &full_bar[warp]);
-            if constexpr (T::NEED_NORMAL) bulk_g2s(s_nrm, P.normals + Pa * DIM, b_pts, &full_bar[warp]);
+            bulk_g2s(s_pts, P.pts + Pa * DIM, b_pts, full_bar_w);
+            bulk_g2s(s_w, P.w + Pa, b_w, full_bar_w);
+            if constexpr (T::NEED_NORMAL) bulk_g2s(s_nrm, P.normals + Pa * DIM, b_pts, full_bar_w);
           }
           if (tail) {
             const int64_t q = Pa + cnt - 1, l = cnt - 1;
@@ -126,7 +101,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         M.w[lane] = staged ? s_w + (o0 - Pa) : P.w + o0;
         if constexpr (T::NEED_NORMAL) M.nrm[lane] = staged ? s_nrm + (o0 - Pa) * DIM : P.normals + o0 * DIM;
         if (ra.valid) {
-          if constexpr (POS_BULK) bulk_g2s(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, &full_bar[warp]);
+          if constexpr (POS_BULK) bulk_g2s(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, full_bar_w);
           if constexpr (Meta::MAT) {
             if constexpr (!POS_BULK) {
               int4* dst = reinterpret_cast<int4*>(&M.pos[lane][0]);
@@ -169,7 +144,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
           M.next = 0;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[warp]);  // release: header + tail stores are visible
+        if (lane == 0) mbar_arrive(full_bar_w);  // release: header + tail stores are visible
       }
       // ---------------- advance the pipeline: A <- B (+ level 3), B <- C (+ level 2), C <- D (+ level 1) ----
       ra = rb;
@@ -226,9 +201,47 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         rc.cell = __ldg(P.cells + k);
       }
     }
+  }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+// MODE 0: G lanes per entry accumulate the element tensor point by point (any form, any cell).
+// MODE 1: G lanes per entry, monomial moments (cq_moment.cuh).
+// MODE 2: one warp per entry, FP64 tensor-core contraction for the Q2 hexahedron (cq_dmma.cuh; G = 32).
+template <class T, int G, int NPW, int NCW, int MODE>
+__global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(const KParams P) {
+  constexpr int CB = 32;
+  constexpr int DIM = T::DIM, N = T::N, NV = T::NV;
+  using Meta = StageMeta<T, CB>;
+  using Lay = StagedLayout<T, CB>;
+  constexpr int CPW = 32 / G;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[NPW], empty_bar[NPW];
+  const int PB = P.stage_points;
+  const size_t stage_bytes = Lay::stage_bytes(PB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NPW; ++s) {
+      mbar_init(&full_bar[s], 2);     // producer lane 0 twice: expect_tx at copy issue, arrive after the header
+      mbar_init(&empty_bar[s], NCW);  // one elected lane per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
+  double msum = 0.0;
+
+  if (warp < NPW) {
+    staged_producer<T, G, CB>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages);
   } else {
     // =========================== consumer warps ===========================================
     const int r = lane & (G - 1), grp = lane / G;
+    LaneEntries<T, G> LE;
+    LE.init(r);
     uint32_t ended = 0, parity = 0;
     int s = 0;
     while (ended != (1u << NPW) - 1u) {
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
             const int e = active ? M.order[e0 + grp] : 0;
             if constexpr (MODE == 2) dmma_process_entry<T, CB>(P, M, e);
             else if constexpr (MODE == 1) moment_process_entry<T, G, CB>(P, M, e, active, r);
-            else staged_process_entry<T, G, CB>(P, M, e, active, r, msum);
+            else staged_process_entry<T, G, CB>(P, M, e, active, r, msum, LE);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -263,5 +276,118 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
   if constexpr (T::RANK == 0) block_sum_atomic(msum, P.out);
 }
 
+
+
+// ---------------------------------------------------------------------------------------------
+// Three-role variant for the moment path (2-D mass / stiffness on axis-aligned cells):
+//   producer warps (as above)  ->  moment warps: point loops, moments into the stage header
+//                              ->  expansion warps: moments -> n x n values -> REDs
+// The expansion is almost pure LSU work (one RED per value, ~1.15 clk per lane per SM measured,
+// profiles/microbench/red_bench.cu) while the point loops are FP64 / latency work; giving them to
+// different warps lets the two overlap instead of alternating inside one warp.  Each expansion warp
+// owns a fixed subset of the x-pairs (compile-time code per role) and handles all 32 entries of a
+// stage with one thread per entry.
+// ---------------------------------------------------------------------------------------------
+template <class T, int G, int NPW, int NMW, int NXW>
+__global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
+  constexpr int CB = 32;
+  using Meta = StageMeta<T, CB>;
+  using Lay = StagedLayout<T, CB>;
+  constexpr int CPW = 32 / G;
+  constexpr int Pn = 2 * T::DEG + 1;
+  static_assert(Meta::MOM, "moment kernel: 2-D mass / stiffness only");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[NPW], mom_bar[NPW], empty_bar[NPW];
+  const int PB = P.stage_points;
+  const size_t stage_bytes = Lay::stage_bytes(PB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NPW; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&mom_bar[s], NMW);
+      mbar_init(&empty_bar[s], NXW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t num_stages = (P.num_entries + CB - 1) / CB;
+
+  if (warp < NPW) {
+    staged_producer<T, G, CB>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages);
+  } else if (warp < NPW + NMW) {
+    // ------------------------------ moment warps ------------------------------
+    const int r = lane & (G - 1), grp = lane / G;
+    uint32_t ended = 0, parity = 0;
+    int s = 0;
+    while (ended != (1u << NPW) - 1u) {
+      if (!((ended >> s) & 1u)) {
+        mbar_wait(&full_bar[s], parity);
+        Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
+        const int nent = M.nent;
+        if (nent < 0) {
+          ended |= 1u << s;
+        } else {
+          for (;;) {
+            int e0 = 0;
+            if (lane == 0) e0 = atomicAdd(&M.next, CPW);
+            e0 = __shfl_sync(0xffffffffu, e0, 0);
+            if (e0 >= nent) break;
+            const bool active = e0 + grp < nent;
+            const int e = active ? M.order[e0 + grp] : 0;
+            double mu[Pn][Pn];
+            moment_accumulate<T, G, CB>(M, e, active, r, mu);
+            if (active) {
+#pragma unroll
+              for (int p = 0; p < Pn; ++p)
+#pragma unroll
+                for (int q = 0; q < Pn; ++q)
+                  if ((p * Pn + q) % G == r) M.mu[p * Pn + q][e] = mu[p][q];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mom_bar[s]);  // also passes the end marker on
+      }
+      if (++s == NPW) {
+        s = 0;
+        parity ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ expansion warps ------------------------------
+    const int xw = warp - NPW - NMW;
+    uint32_t ended = 0, parity = 0;
+    int s = 0;
+    while (ended != (1u << NPW) - 1u) {
+      if (!((ended >> s) & 1u)) {
+        mbar_wait(&mom_bar[s], parity);
+        Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
+        const int nent = M.nent;
+        if (nent < 0) {
+          ended |= 1u << s;
+        } else {
+          if (lane < nent && P.dbg != 2) {
+            double mu[Pn][Pn];
+#pragma unroll
+            for (int p = 0; p < Pn; ++p)
+#pragma unroll
+              for (int q = 0; q < Pn; ++q) mu[p][q] = M.mu[p * Pn + q][lane];
+            static_for<0, NXW>([&](auto XW) {
+              if (xw == decltype(XW)::value) moment_expand<T, 1, CB, decltype(XW)::value, NXW>(P, M, lane, 0, mu);
+            });
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+      }
+      if (++s == NPW) {
+        s = 0;
+        parity ^= 1;
+      }
+    }
+  }
+}
 
 }  // namespace cq
