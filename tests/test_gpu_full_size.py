@@ -1,0 +1,162 @@
+"""BASELINE.json-size checks of the CUDA path (parity on the full problem through
+size-independent properties + the oracle on a fixed random sample of >= 65,536 cells assembled into the
+same sparsity).  Properties used: constants are in the kernel of the stiffness matrix (row sums 0), the
+mass matrix integrates 1 (sum of entries = sum_c |K_c| sum_q w_q), symmetry (x'Ay = y'Ax), linearity
+in the weights, and for scalars sum w = measure."""
+import numpy as np
+import pytest
+import torch
+
+import customquad_b200 as cq
+from customquad_b200 import assemble as asm
+from customquad_b200 import forms
+from customquad_b200.quadrature import synthetic_ragged
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _row_sums(A):
+    rows = torch.repeat_interleave(torch.arange(A.shape[0], device=A.data.device), A.indptr[1:] - A.indptr[:-1])
+    return torch.zeros(A.shape[0], dtype=torch.float64, device=A.data.device).index_add_(0, rows, A.data)
+
+
+def _spmv(A, x):
+    M = torch.sparse_csr_tensor(A.indptr, A.indices.to(torch.int64), A.data, size=A.shape)
+    return M @ x
+
+
+def _sample_parity(form, qr, A, sample, oracle, bs=1):
+    """Oracle on `sample` entries of the rule vs the CUDA assembly of the same entries into the full
+    pattern: compare every (row, col) the oracle produced."""
+    sub = qr.select(sample)
+    B = asm.create_matrix(form)
+    cq.assemble_matrix(form, [sub], A=B)
+    B.assemble()
+    R = oracle.assemble_matrix(form, [sub], nthreads=oracle.max_threads(), pattern=_cells_pattern(form, sub)).tocoo()
+    keep = R.data != 0.0
+    rr, cc, vv = R.row[keep].astype(np.int64), R.col[keep].astype(np.int64), R.data[keep]
+    # look the oracle's (row, col) up in the device CSR
+    ip = B.indptr.cpu().numpy()
+    ix = B.indices.cpu().numpy()
+    data = B.data.cpu().numpy()
+    pos = np.empty(len(rr), dtype=np.int64)
+    for k in range(0, len(rr), 1 << 20):  # vectorised row-wise search in chunks
+        r, c = rr[k : k + (1 << 20)], cc[k : k + (1 << 20)]
+        lo, hi = ip[r].copy(), ip[r + 1].copy()
+        while np.any(lo < hi):
+            mid = (lo + hi) // 2
+            act = lo < hi
+            less = np.zeros_like(act)
+            less[act] = ix[mid[act]] < c[act]
+            lo = np.where(act & less, mid + 1, lo)
+            hi = np.where(act & ~less, mid, hi)
+        assert np.array_equal(ix[lo], c), "sparsity mismatch"
+        pos[k : k + (1 << 20)] = lo
+    got = data[pos]
+    assert np.linalg.norm(got - vv) <= RTOL * np.linalg.norm(vv)
+    assert np.max(np.abs(got - vv)) <= RTOL * np.max(np.abs(vv))
+    # and nothing else was touched
+    assert abs(np.abs(data).sum() - np.abs(got).sum()) <= 1e-9 * np.abs(got).sum()
+
+
+def _cells_pattern(form, sub):
+    from customquad_b200.sparsity import build_pattern
+
+    V = form.function_spaces[0]
+    return build_pattern(V.dofmap.list, V.dofmap.num_dofs, V.bs, cells=sub.cells)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_config2_full_size(cuda_backend, degree):
+    """BASELINE.json configs[1]: 2048 x 2048 quads, ragged U{16..64} rules, all cells."""
+    from oracle import oracle
+
+    N = 2048
+    mesh = cq.create_rectangle([[-1.11, -1.51], [1.55, 1.22]], [N, N])
+    V = cq.FunctionSpace(mesh, ("Lagrange", degree))
+    qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 2, 16, 64, seed=20231)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.rand(V.num_dofs, dtype=torch.float64, device=dev, generator=g)
+    y = torch.rand(V.num_dofs, dtype=torch.float64, device=dev, generator=g)
+    cell_vol = float(np.prod(mesh.h()))
+    sw = np.add.reduceat(qr.w, qr.offsets[:-1])  # sum of weights per cell
+
+    K = cq.assemble_matrix(forms.stiffness(V), [qr])
+    K.assemble()
+    assert float(_row_sums(K).abs().max()) <= RTOL * float(K.data.abs().max()) * 25  # constants in the kernel
+    assert abs(float(x @ _spmv(K, y)) - float(y @ _spmv(K, x))) <= RTOL * abs(float(x @ _spmv(K, y)))
+    M = cq.assemble_matrix(forms.mass(V), [qr])
+    M.assemble()
+    total = float(M.data.sum())
+    assert abs(total - cell_vol * sw.sum()) <= RTOL * abs(total)  # integrates 1
+    assert abs(float(x @ _spmv(M, y)) - float(y @ _spmv(M, x))) <= RTOL * abs(float(x @ _spmv(M, y)))
+    # linearity in the weights: doubling them doubles the matrix
+    q2 = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 2, 16, 64, seed=20231)
+    q2.w *= 2.0
+    K2 = cq.assemble_matrix(forms.stiffness(V), [q2])
+    K2.assemble()
+    assert float((K2.data - 2.0 * K.data).abs().max()) <= RTOL * float(K.data.abs().max())
+    del K2, q2
+    # oracle on a fixed random sample of 65,536 cells (seeded), both forms
+    sample = np.sort(np.random.default_rng(7).choice(mesh.num_cells, 65536, replace=False))
+    _sample_parity(forms.stiffness(V), qr, K, sample, oracle)
+    _sample_parity(forms.mass(V), qr, M, sample, oracle)
+
+
+def test_config3_shape_hex_q1(cuda_backend):
+    """BASELINE.json configs[2] shape: Q1 hexahedra, cut-cell volume rules U{8..27} and surface rules
+    with normals; 128^3 here (the 256^3 pattern needs 5.5 GB of setup; same kernels)."""
+    from oracle import oracle
+
+    mesh = cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [128, 128, 128])
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    rng = np.random.default_rng(3)
+    cut = np.sort(rng.choice(mesh.num_cells, 200000, replace=False)).astype(np.int32)  # ~2e5 cut cells (cfg 3)
+    qb = synthetic_ragged(cut, 3, 8, 27, seed=11)
+    qs = synthetic_ragged(cut, 3, 4, 16, seed=12, normals=True)
+    vol = cq.assemble_scalar(forms.integral(mesh, 1.0), [qb])
+    sw = np.add.reduceat(qb.w, qb.offsets[:-1]).sum()
+    assert abs(vol - float(np.prod(mesh.h())) * sw) <= RTOL * abs(vol)
+    K = cq.assemble_matrix(forms.stiffness(V), [qb])
+    K.assemble()
+    assert float(_row_sums(K).abs().max()) <= RTOL * float(K.data.abs().max()) * 27
+    Nm = cq.assemble_matrix(forms.nitsche(V, 10.0), [qs])
+    Nm.assemble()
+    dev = K.data.device
+    x = torch.rand(V.num_dofs, dtype=torch.float64, device=dev)
+    y = torch.rand(V.num_dofs, dtype=torch.float64, device=dev)
+    assert abs(float(x @ _spmv(Nm, y)) - float(y @ _spmv(Nm, x))) <= 1e-11 * abs(float(x @ _spmv(Nm, y)))  # symmetric Nitsche form
+    sample = np.sort(rng.choice(len(cut), 65536, replace=False))
+    _sample_parity(forms.stiffness(V), qb, K, sample, oracle)
+    _sample_parity(forms.nitsche(V, 10.0), qs, Nm, sample, oracle)
+    b = cq.assemble_vector(forms.nitsche_rhs(V, cq.Analytic.sinprod(1.0), 10.0), [qs]).array
+    r = oracle.assemble_vector(forms.nitsche_rhs(V, cq.Analytic.sinprod(1.0), 10.0), [qs], nthreads=oracle.max_threads())
+    assert np.max(np.abs(b - r)) <= RTOL * np.max(np.abs(r))
+
+
+def test_config4_shape_hex_q2_vector(cuda_backend):
+    """BASELINE.json configs[3] shape: vector Poisson on Q2 hexahedra (bs = 3), 3^3 Gauss points per
+    cell; 24^3 here (same kernels: FP64 tensor-core path + blocked scatter)."""
+    from customquad_b200.quadrature import gauss_tensor_rule
+    from oracle import oracle
+
+    mesh = cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [24, 24, 24])
+    V = cq.VectorFunctionSpace(mesh, ("Lagrange", 2))
+    pts, w = gauss_tensor_rule(3, 4)
+    C = mesh.num_cells
+    qr = cq.quadrature.normalise_qr((np.arange(C), np.tile(pts.reshape(-1), [C, 1]), np.tile(w, [C, 1])), 3)
+    K = cq.assemble_matrix(forms.stiffness(V), [qr])
+    K.assemble()
+    assert float(_row_sums(K).abs().max()) <= 1e-11 * float(K.data.abs().max())  # rigid translations
+    M = cq.assemble_matrix(forms.mass(V), [qr])
+    M.assemble()
+    vol = float(np.prod(np.asarray(mesh.xmax) - np.asarray(mesh.xmin)))
+    assert abs(float(M.data.sum()) - 3 * vol) <= 1e-11 * 3 * vol  # exact rule: each component integrates 1
+    sample = np.sort(np.random.default_rng(2).choice(C, 4096, replace=False))
+    _sample_parity(forms.stiffness(V), qr, K, sample, oracle, bs=3)
+    f = cq.Analytic.sinprod(2 * np.pi**2, 0.0, 0.0)  # demo/vector_poisson.py f
+    b = cq.assemble_vector(forms.load(V, f), [qr]).array
+    r = oracle.assemble_vector(forms.load(V, f), [qr], nthreads=oracle.max_threads())
+    assert np.max(np.abs(b - r)) <= RTOL * np.max(np.abs(r))
