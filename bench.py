@@ -355,7 +355,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--forms", default="", help="development only: comma-separated subset of the workload's forms (changes the workload; shown in config.forms)")
     args = ap.parse_args()
+    if args.forms:
+        global FORMS
+        FORMS = [f for f in FORMS if f[0] in args.forms.split(",")]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -48,6 +48,8 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   P.stage_points = (int)pb;
   static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
   P.dbg = dbg;
+  static const int pf = getenv("CQ_PREFETCH") ? atoi(getenv("CQ_PREFETCH")) : 0;  // in units of the grid size
+  P.prefetch_stages = pf * ctx->num_sms;
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
   static thread_local size_t configured = 0;  // per kernel instantiation
   if (smem > configured) {
@@ -62,11 +64,11 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
 }
 
-template <class T, int G, int NPW, int NMW, int NXW>
+template <class T, int G, int NPW, int NMW, int NXW, bool XT = false>
 static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   constexpr int CB = 32;
   using Lay = StagedLayout<T, CB>;
-  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW>;
+  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW, XT>;
   const size_t budget = (size_t)ctx->max_smem_optin - 1024;
   const size_t per_point = (size_t)T::DIM * 8 + 8;
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
@@ -77,9 +79,17 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   pb = (pb + 1) & ~(int64_t)1;
   if (pb > pb_max) pb = pb_max;
   if (pb < 64) pb = 64;
+  if constexpr (XT) {
+    // the expansion tiles of a stage reuse its point buffer: it has to hold (DEG + 1) of them
+    const int64_t need = (int64_t)(((T::DEG + 1) * RowTile<T::DEG>::bytes(CB) + T::DIM * 8 - 1) / (T::DIM * 8));
+    if (pb < need) pb = (need + 1) & ~(int64_t)1;
+    if (pb > pb_max) { set_error("moment kernel: expansion tiles do not fit the stage"); return CQ_ERR_UNSUPPORTED; }
+  }
   P.stage_points = (int)pb;
   static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
   P.dbg = dbg;
+  static const int pf = getenv("CQ_PREFETCH") ? atoi(getenv("CQ_PREFETCH")) : 0;  // in units of the grid size
+  P.prefetch_stages = pf * ctx->num_sms;
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
   static thread_local size_t configured = 0;
   if (smem > configured) {
@@ -108,6 +118,21 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NPW
 #define CQ_MOMENT_NPW 4
 #endif
+#ifndef CQ_MOMENT_NMW
+#define CQ_MOMENT_NMW 8
+#endif
+#ifndef CQ_MOMENT_NXW1
+#define CQ_MOMENT_NXW1 3
+#endif
+#ifndef CQ_MOMENT_SG
+#define CQ_MOMENT_SG 4
+#endif
+#ifndef CQ_MOMENT_NXS1  // expansion warp sets, degree 1
+#define CQ_MOMENT_NXS1 1
+#endif
+#ifndef CQ_MOMENT_NXS2  // expansion warp sets, degree 2
+#define CQ_MOMENT_NXS2 2
+#endif
 // mesh flags (cq_mesh.flags)
 constexpr int MESH_AXIS_ALIGNED = 1;
 
@@ -120,8 +145,10 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
       if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) {
         // three-role kernel for Q1 (measured 1.00 vs 1.06 ms on the bench workload); for Q2 both
         // organisations are bound by the L2 atomic rate of the 81 REDs per cell (2.56 vs 2.59 ms)
-        static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : (T::DEG == 1 ? 1 : 0);
-        if (split) return launch_moment_split<T, 4, 4, 8, T::DEG == 1 ? 2 : 3>(ctx, P, s);
+        // split = 2: row-owned expansion + transposed scatter (RowTile, cq_moment.cuh)
+        static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : 2;
+        if (split == 2) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1), true>(ctx, P, s);
+        if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1>(ctx, P, s);
         return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
       }
     }

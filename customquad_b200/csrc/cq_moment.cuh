@@ -126,7 +126,7 @@ CQ_HD constexpr int pair_owner(int idx) {
 // T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}.
 // Point loop: G lanes per entry, lane r takes the points r, r+G, ...; the moments are all-reduced over
 // the group (every lane ends with the full set).
-template <class T, int G, int CB>
+template <class T, int G, int CB, bool ALLREDUCE = true>
 CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const bool active, const int r,
                                  double (&mu)[2 * T::DEG + 1][2 * T::DEG + 1]) {
   constexpr int Pn = 2 * T::DEG + 1;
@@ -157,13 +157,32 @@ CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const b
 #pragma unroll
       for (int q2 = 0; q2 < Pn; ++q2) mu[p][q2] = fma(X[p], WY[q2], mu[p][q2]);
   }
-  if constexpr (G > 1) {
+  if constexpr (G > 1 && ALLREDUCE) {
 #pragma unroll
     for (int st = G / 2; st >= 1; st >>= 1)
 #pragma unroll
       for (int p = 0; p < Pn; ++p)
 #pragma unroll
         for (int q = 0; q < Pn; ++q) mu[p][q] += __shfl_xor_sync(0xffffffffu, mu[p][q], st);
+  }
+}
+
+// Split kernels: the moments of an entry go to the stage header, so instead of an all-reduce the
+// G lanes transpose-reduce (M (1 - 1/G) shuffles) and lane r stores its slice of the sums.
+template <class T, int G, int CB>
+CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const bool active, const bool compute, const int r) {
+  constexpr int Pn = 2 * T::DEG + 1, NM = Pn * Pn;
+  constexpr int MPAD = round_up(NM, G), B = MPAD / G;
+  double mu[Pn][Pn];
+  moment_accumulate<T, G, CB, false>(M, e, active && compute, r, mu);
+  double acc[MPAD];
+#pragma unroll
+  for (int k = 0; k < MPAD; ++k) acc[k] = k < NM ? mu[k / Pn][k % Pn] : 0.0;
+  transpose_reduce_step<MPAD, G / 2>(acc, r);
+  if (active) {
+#pragma unroll
+    for (int kk = 0; kk < B; ++kk)
+      if (r * B + kk < NM) M.mu[r * B + kk][e] = acc[kk];
   }
 }
 
@@ -233,6 +252,127 @@ CQ_DEVINL void moment_expand_comp(const KParams& P, const StageMeta<T, CB>& M, c
       }
     });
   });
+}
+
+// ---- row-owned expansion + transposed scatter --------------------------------------------------
+// Measured on the bench workload (profiles/r1/scatter_study.md): a RED (or a plain store) whose 32
+// lanes go to 32 different rows costs one L1 tag cycle per lane, i.e. 81 * 32 cycles per stage for
+// Q2 -- 1.2 ms of the 2.5 ms kernel -- whatever the L2 does.  With lane = entry (above) that is the
+// access pattern.  Here an expansion warp owns the rows whose x lattice index is A0: it forms their
+// (DEG+1) * N values per entry with lane = entry, parks them in a shared-memory tile (the stage's
+// point buffer, dead once the moments are done), and scatters the tile with lane = position inside
+// the tile: consecutive lanes hold consecutive columns (c1 fastest) of one row, which are adjacent
+// CSR slots whenever the dofs along the points' axis 1 are numbered consecutively (dolfinx
+// create_rectangle is y-fastest) -> one sector per run of DEG+1 values (ncu: 2.5x fewer RED sectors,
+// 5x fewer L1 wavefronts).  The scatter loop is unrolled over the entries so that every address is
+// base + constant.
+template <int DEG>
+struct RowTile {
+  static constexpr int D1 = DEG + 1, N = D1 * D1;
+  static constexpr int NVW = D1 * N;        // values per entry owned by one expansion warp
+  static constexpr int STRIDE = NVW | 1;    // odd stride: conflict-free one-thread-per-entry writes
+  static constexpr int EPI = 32 / NVW;      // entries per scatter instruction (Q1: 4, Q2: 1)
+  static constexpr size_t bytes(int cb) { return (size_t)cb * STRIDE * 8; }
+  // local dof of lattice point (x, y), 4 bits each, index x * D1 + y
+  CQ_HD static constexpr uint64_t dof_table() {
+    uint64_t t = 0;
+    for (int x = 0; x < D1; ++x)
+      for (int y = 0; y < D1; ++y) t |= (uint64_t)quad_dof_of<DEG>(x, y) << (4 * (x * D1 + y));
+    return t;
+  }
+};
+
+// lane = entry e: values (a1, c0, c1) of the rows with x index A0 -> tile[(a1 * D1 + c0) * D1 + c1]
+template <class T, int CB, int A0>
+CQ_DEVINL void moment_expand_rows(const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
+  constexpr int DEG = T::DEG, D1 = DEG + 1;
+  using Q = Poly1D<DEG>;
+  constexpr int Pn = Q::P;
+  constexpr bool STIFF = T::FORM_ID == CQ_FORM_STIFFNESS;
+  double mu[Pn][Pn];
+#pragma unroll
+  for (int p = 0; p < Pn; ++p)
+#pragma unroll
+    for (int q = 0; q < Pn; ++q) mu[p][q] = M.mu[p * Pn + q][e];
+  const double k0 = STIFF ? M.kc[1][e] : M.kc[0][e];  // stiffness: |det|/J00^2 ; mass: |det|
+  const double k1 = STIFF ? M.kc[2][e] : 0.0;         // stiffness: |det|/J11^2
+  static_for<0, D1>([&](auto C0) {
+    constexpr int c0 = decltype(C0)::value;
+    // contract the x index; the first non-zero term initialises (no 0 + x instructions)
+    double U0[Pn], U1[Pn];
+    bool i0 = false, i1 = false;
+    static_for<0, Pn>([&](auto PP) {
+      constexpr int p = decltype(PP)::value;
+      constexpr double r00 = Q::R00(A0, c0, p), r11 = Q::R11(A0, c0, p);
+      if constexpr (r00 != 0.0) {
+#pragma unroll
+        for (int q = 0; q < Pn; ++q) U0[q] = i0 ? fma(r00, mu[p][q], U0[q]) : r00 * mu[p][q];
+        i0 = true;
+      }
+      if constexpr (STIFF && r11 != 0.0) {
+#pragma unroll
+        for (int q = 0; q < Pn; ++q) U1[q] = i1 ? fma(r11, mu[p][q], U1[q]) : r11 * mu[p][q];
+        i1 = true;
+      }
+    });
+    static_for<0, D1>([&](auto A1) {
+      static_for<0, D1>([&](auto C1) {
+        constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
+        double m0 = 0.0, m1 = 0.0;
+        bool j0 = false, j1 = false;
+        static_for<0, Pn>([&](auto QQ) {
+          constexpr int q = decltype(QQ)::value;
+          constexpr double r00 = Q::R00(a1, c1, q), r11 = Q::R11(a1, c1, q);
+          if constexpr (STIFF) {
+            if constexpr (r00 != 0.0) { m0 = j0 ? fma(r00, U1[q], m0) : r00 * U1[q]; j0 = true; }  // d/dx d/dx
+            if constexpr (r11 != 0.0) { m1 = j1 ? fma(r11, U0[q], m1) : r11 * U0[q]; j1 = true; }  // d/dy d/dy
+          } else {
+            if constexpr (r00 != 0.0) { m0 = j0 ? fma(r00, U0[q], m0) : r00 * U0[q]; j0 = true; }
+          }
+        });
+        tile[(a1 * D1 + c0) * D1 + c1] = STIFF ? fma(k0, m0, k1 * m1) : k0 * m0;
+      });
+    });
+  });
+}
+
+// All 32 lanes.  tile: nent entries of RowTile::NVW values at stride RowTile::STRIDE.  Lane ->
+// (entry within the instruction, value slot) is loop invariant; lanes beyond EPI * NVW idle.
+template <class T, int CB, int A0>
+CQ_DEVINL void scatter_rows_transposed(const KParams& P, const StageMeta<T, CB>& M, const double* __restrict__ tile, const int nent,
+                                       const int lane) {
+  using RT = RowTile<T::DEG>;
+  constexpr int D1 = RT::D1, N = RT::N, NVW = RT::NVW, EPI = RT::EPI;
+  constexpr uint64_t TBL = RT::dof_table();
+  const int sub = lane / NVW, s = lane - sub * NVW;
+  if (sub >= EPI) return;
+  const int a1 = s / N, cc = s - a1 * N;  // cc = c0 * D1 + c1
+  const int i = (int)((TBL >> (4 * (A0 * D1 + a1))) & 15u), j = (int)((TBL >> (4 * cc)) & 15u);
+  const double* tl = tile + sub * RT::STRIDE + s;
+  const uint8_t* pp = &M.pos[sub][i * N + j];
+  const long long* rs = &M.rowstart[i][sub];
+  double* const vals = P.values;
+  if (P.bs == 1) {
+    if (nent == CB) {
+#pragma unroll
+      for (int e0 = 0; e0 < CB; e0 += EPI)
+        red_add_f64(vals + rs[e0] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
+    } else {
+#pragma unroll 1
+      for (int e0 = 0; e0 + sub < nent; e0 += EPI)
+        red_add_f64(vals + rs[e0] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
+    }
+  } else {
+    const int bs = P.bs;
+    const int* rl = &M.rowlen[i][sub];
+#pragma unroll 1
+    for (int e0 = 0; e0 + sub < nent; e0 += EPI) {
+      const double v = tl[e0 * RT::STRIDE];
+      double* row = vals + rs[e0] + (unsigned)pp[e0 * StageMeta<T, CB>::NPOS] * bs;
+      const int len = rl[e0];
+      for (int a = 0; a < bs; ++a) red_add_f64(row + (long long)a * len + a, v);
+    }
+  }
 }
 
 // bs == 1: unit-stride scatter; blocked spaces: the scalar block is scattered once per component

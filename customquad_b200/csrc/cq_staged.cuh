@@ -57,6 +57,11 @@ CQ_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, ui
                : "memory");
 }
 
+// L2 prefetch of a global range; bytes % 16 == 0, address 16-B aligned
+CQ_DEVINL void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ---- stage layout ------------------------------------------------------------------------------------
 template <class T, int CB>
 struct StageMeta {
@@ -82,6 +87,7 @@ struct StageMeta {
   static constexpr bool MOM = T::DIM == 2 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS);
   static constexpr int NMOM = MOM ? (2 * T::DEG + 1) * (2 * T::DEG + 1) : 1;
   double mu[NMOM][CB];
+  double kc[MOM ? 3 : 1][CB];  // axis-aligned cell constants: |det J|, |det J|/J00^2, |det J|/J11^2 (producer)
 };
 
 template <class T, int CB>

@@ -24,7 +24,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
     double* s_pts = reinterpret_cast<double*>(base + Lay::meta_bytes);
     double* s_w = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB));
     double* s_nrm = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB) + Lay::w_bytes(PB));
-    constexpr bool POS_BULK = Meta::MAT && Meta::NPOS > 128;  // large rows: bulk copy instead of registers
+    constexpr bool POS_BULK = Meta::MAT && Meta::NPOS > 64;  // larger maps: bulk copy instead of registers
     constexpr int NP16 = (Meta::MAT && !POS_BULK) ? Meta::NPOS / 16 : 1;
     struct Regs {
       long long t;  // stage index; -2: pipeline bubble, -1: no more work
@@ -38,6 +38,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
       double X[NV * DIM];
       long long rs[Meta::MAT ? N : 1];
       int rl[Meta::MAT ? N : 1];
+      int64_t pf0, pf1;  // lane 0: point range of the stage `prefetch_stages` ahead (L2 prefetch)
     };
     Regs ra, rb, rc;
     ra.t = rb.t = rc.t = -2;
@@ -116,6 +117,15 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           }
 #pragma unroll
           for (int i = 0; i < NV * DIM; ++i) M.X[i][lane] = ra.X[i];
+          if constexpr (Meta::MOM) {
+            // J = diag(J00, J11): local vertex 2 is the +x neighbour, local vertex 1 the +y neighbour (Lattice<2,1>)
+            const double J00 = ra.X[2 * 2 + 0] - ra.X[0], J11 = ra.X[1 * 2 + 1] - ra.X[1];
+            M.kc[0][lane] = fabs(J00 * J11);
+            if constexpr (T::FORM_ID == CQ_FORM_STIFFNESS) {
+              M.kc[1][lane] = fabs(J11 / J00);
+              M.kc[2][lane] = fabs(J00 / J11);
+            }
+          }
           if constexpr (Meta::VEC) {
 #pragma unroll
             for (int i = 0; i < N; ++i) M.dofs[i][lane] = ra.dof[i];
@@ -164,6 +174,17 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         }
       }
       rb = rc;
+      // The stages in shared memory cover ~1 us of DRAM latency only while all of them are in their
+      // copy phase; prefetching the point slice of a stage far ahead into L2 keeps DRAM busy
+      // independently of how long the compute phases hold the stage slots.
+      if (rb.t >= 0 && lane == 0 && rb.pf1 > rb.pf0) {
+        const int64_t a = rb.pf0 & ~(int64_t)1, b = rb.pf1 & ~(int64_t)1;
+        if (b > a) {
+          bulk_prefetch_l2(P.pts + a * DIM, (uint32_t)((b - a) * DIM * 8));
+          bulk_prefetch_l2(P.w + a, (uint32_t)((b - a) * 8));
+          if constexpr (T::NEED_NORMAL) bulk_prefetch_l2(P.normals + a * DIM, (uint32_t)((b - a) * DIM * 8));
+        }
+      }
       if (rb.t >= 0 && rb.valid) {
         const int32_t cell = rb.cell;
         if constexpr (DIM == 2) {
@@ -199,6 +220,13 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         rc.o0 = __ldg(P.offsets + k);
         rc.o1 = __ldg(P.offsets + k + 1);
         rc.cell = __ldg(P.cells + k);
+        rc.pf0 = rc.pf1 = 0;
+        const int64_t tp = td + P.prefetch_stages;
+        if (lane == 0 && P.prefetch_stages > 0 && tp < num_stages) {
+          const int64_t kp = tp * CB, kq = (kp + CB) < P.num_entries ? (kp + CB) : P.num_entries;
+          rc.pf0 = __ldg(P.offsets + kp);
+          rc.pf1 = __ldg(P.offsets + kq);
+        }
       }
     }
   }
@@ -288,7 +316,8 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
 // owns a fixed subset of the x-pairs (compile-time code per role) and handles all 32 entries of a
 // stage with one thread per entry.
 // ---------------------------------------------------------------------------------------------
-template <class T, int G, int NPW, int NMW, int NXW>
+// XT: row-owned expansion with the transposed scatter (RowTile, cq_moment.cuh); NXW = sets * (DEG + 1)
+template <class T, int G, int NPW, int NMW, int NXW, bool XT = false>
 __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
   constexpr int CB = 32;
   using Meta = StageMeta<T, CB>;
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
     for (int s = 0; s < NPW; ++s) {
       mbar_init(&full_bar[s], 2);
       mbar_init(&mom_bar[s], NMW);
-      mbar_init(&empty_bar[s], NXW);
+      mbar_init(&empty_bar[s], XT ? T::DEG + 1 : NXW);  // the expansion warps of one set
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -336,15 +365,7 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
             if (e0 >= nent) break;
             const bool active = e0 + grp < nent;
             const int e = active ? M.order[e0 + grp] : 0;
-            double mu[Pn][Pn];
-            moment_accumulate<T, G, CB>(M, e, active, r, mu);
-            if (active) {
-#pragma unroll
-              for (int p = 0; p < Pn; ++p)
-#pragma unroll
-                for (int q = 0; q < Pn; ++q)
-                  if ((p * Pn + q) % G == r) M.mu[p * Pn + q][e] = mu[p][q];
-            }
+            moment_accumulate_store<T, G, CB>(M, e, active, P.dbg != 1, r);
           }
         }
         __syncwarp();
@@ -357,18 +378,41 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
     }
   } else {
     // ------------------------------ expansion warps ------------------------------
+    // XT: warp = (set, role); role = x lattice index of the rows it owns, set k serves the stage
+    // slots s with s % NXS == k (NXS = NXW / (DEG + 1) sets work on different stages concurrently)
+    constexpr int NROLE = XT ? T::DEG + 1 : NXW;
+    constexpr int NXS = NXW / NROLE;
+    static_assert(NXW % NROLE == 0 && NPW % NXS == 0, "expansion warps: whole sets, slots divisible by sets");
     const int xw = warp - NPW - NMW;
+    const int role = xw % NROLE, set = xw / NROLE;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < NPW; ++q)
+      if (q % NXS == set) mine |= 1u << q;
     uint32_t ended = 0, parity = 0;
     int s = 0;
-    while (ended != (1u << NPW) - 1u) {
-      if (!((ended >> s) & 1u)) {
+    while (ended != mine) {
+      if (((mine >> s) & 1u) && !((ended >> s) & 1u)) {
         mbar_wait(&mom_bar[s], parity);
         Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
         const int nent = M.nent;
         if (nent < 0) {
           ended |= 1u << s;
         } else {
-          if (lane < nent && P.dbg != 2) {
+          if constexpr (XT) {
+            // this warp's tile lives in the stage's point buffer (dead after the moment phase)
+            using RT = RowTile<T::DEG>;
+            double* tile = reinterpret_cast<double*>(smem_raw + (size_t)s * stage_bytes + Lay::meta_bytes + (size_t)role * RT::bytes(CB));
+            if (P.dbg != 2) {
+              static_for<0, T::DEG + 1>([&](auto RR) {
+                if (role == decltype(RR)::value) {
+                  if (lane < nent) moment_expand_rows<T, CB, decltype(RR)::value>(M, lane, tile + lane * RT::STRIDE);
+                  __syncwarp();
+                  scatter_rows_transposed<T, CB, decltype(RR)::value>(P, M, tile, nent, lane);
+                }
+              });
+            }
+          } else if (lane < nent && P.dbg != 2) {
             double mu[Pn][Pn];
 #pragma unroll
             for (int p = 0; p < Pn; ++p)
