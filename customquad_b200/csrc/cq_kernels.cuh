@@ -34,7 +34,6 @@ struct KParams {
   unsigned int* work_counter;            // ctx-owned, zeroed before a staged launch
   int64_t num_points;                    // length of pts / w (bulk-copy tail handling)
   int stage_points;                      // points capacity of one smem stage
-  int prefetch_stages;                   // staged kernels: L2 prefetch distance in stages (0 = off)
   int mesh_flags;                        // cq_mesh.flags
   int dbg;                               // profiling experiments only (CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)

@@ -48,15 +48,12 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   P.stage_points = (int)pb;
   static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
   P.dbg = dbg;
-  static const int pf = getenv("CQ_PREFETCH") ? atoi(getenv("CQ_PREFETCH")) : 0;  // in units of the grid size
-  P.prefetch_stages = pf * ctx->num_sms;
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
   static thread_local size_t configured = 0;  // per kernel instantiation
   if (smem > configured) {
     if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
     configured = smem;
   }
-  if (int rc = check_cuda(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s), "work_counter reset")) return rc;
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
   kernel<<<grid, (NPW + NCW) * 32, smem, s>>>(P);
@@ -64,11 +61,11 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
 }
 
-template <class T, int G, int NPW, int NMW, int NXW, bool XT = false>
+template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1>
 static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   constexpr int CB = 32;
   using Lay = StagedLayout<T, CB>;
-  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW, XT>;
+  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW, XT, NPP>;
   const size_t budget = (size_t)ctx->max_smem_optin - 1024;
   const size_t per_point = (size_t)T::DIM * 8 + 8;
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
@@ -88,18 +85,15 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   P.stage_points = (int)pb;
   static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
   P.dbg = dbg;
-  static const int pf = getenv("CQ_PREFETCH") ? atoi(getenv("CQ_PREFETCH")) : 0;  // in units of the grid size
-  P.prefetch_stages = pf * ctx->num_sms;
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
   static thread_local size_t configured = 0;
   if (smem > configured) {
     if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
     configured = smem;
   }
-  if (int rc = check_cuda(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s), "work_counter reset")) return rc;
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
-  kernel<<<grid, (NPW + NMW + NXW) * 32, smem, s>>>(P);
+  kernel<<<grid, (NPW * NPP + NMW + NXW) * 32, smem, s>>>(P);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "assemble_moment_split_kernel launch");
 }
@@ -127,6 +121,9 @@ struct StagedShape {
 #ifndef CQ_MOMENT_SG
 #define CQ_MOMENT_SG 4
 #endif
+#ifndef CQ_MOMENT_NPP  // producer warps per stage slot
+#define CQ_MOMENT_NPP 1
+#endif
 #ifndef CQ_MOMENT_NXS1  // expansion warp sets, degree 1
 #define CQ_MOMENT_NXS1 1
 #endif
@@ -147,7 +144,7 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // organisations are bound by the L2 atomic rate of the 81 REDs per cell (2.56 vs 2.59 ms)
         // split = 2: row-owned expansion + transposed scatter (RowTile, cq_moment.cuh)
         static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : 2;
-        if (split == 2) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1), true>(ctx, P, s);
+        if (split == 2) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1), true, CQ_MOMENT_NPP>(ctx, P, s);
         if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1>(ctx, P, s);
         return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
       }

@@ -57,11 +57,6 @@ CQ_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, ui
                : "memory");
 }
 
-// L2 prefetch of a global range; bytes % 16 == 0, address 16-B aligned
-CQ_DEVINL void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-
 // ---- stage layout ------------------------------------------------------------------------------------
 template <class T, int CB>
 struct StageMeta {

@@ -9,7 +9,8 @@ namespace cq {
 // ---- producer role (one warp per stage slot) ----------------------------------------------------------
 template <class T, int G, int CB>
 CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* full_bar_w, uint64_t* empty_bar_w, const int lane,
-                               const int PB, const int64_t num_stages) {
+                               const int PB, const int64_t num_stages, const int slot, const int nslots, const int sub = 0,
+                               const int npp = 1, uint64_t* turn_bar_w = nullptr) {
   constexpr int DIM = T::DIM, N = T::N, NV = T::NV;
   using Meta = StageMeta<T, CB>;
   using Lay = StagedLayout<T, CB>;
@@ -38,21 +39,28 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
       double X[NV * DIM];
       long long rs[Meta::MAT ? N : 1];
       int rl[Meta::MAT ? N : 1];
-      int64_t pf0, pf1;  // lane 0: point range of the stage `prefetch_stages` ahead (L2 prefetch)
     };
     Regs ra, rb, rc;
     ra.t = rb.t = rc.t = -2;
     ra.valid = rb.valid = rc.valid = false;
-    // the work counter is read one iteration ahead: lane 0 keeps the raw ticket, the broadcast
-    // (which has to wait for the atomic's round trip) happens at the next advance
-    unsigned int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(P.work_counter, 1u);
-    uint32_t parity = 0;
-    bool first = true;
+    // Stages are dealt out statically, interleaved over the CTAs and their slots: with hundreds of
+    // stages per CTA the ragged rules average out (a dynamic ticket costs one more dependent
+    // round trip per stage in this latency-bound warp).
+    // With npp > 1 producer warps per slot, warp `sub` fills the slot's rounds sub, sub + npp, ...: its
+    // gather chain overlaps the other warps' rounds.  Round r of a slot may be written once round
+    // r - 1 has been published (turn barrier) and consumed (empty barrier).
+    const int64_t round_t = (int64_t)nslots * gridDim.x;
+    int64_t next_t = ((int64_t)sub * nslots + slot) * gridDim.x + blockIdx.x;
+    const int64_t step_t = round_t * npp;
+    int round = sub;
     for (;;) {
       // ---------------- publish stage A ----------------
+      if (ra.t == -3) break;  // beyond the end marker (another warp of this slot publishes it)
       if (ra.t == -1) {
-        if (!first) mbar_wait(empty_bar_w, parity);
+        if (round >= 1) {
+          if (npp > 1) mbar_wait(turn_bar_w, (uint32_t)(round - 1) & 1u);
+          mbar_wait(empty_bar_w, (uint32_t)(round - 1) & 1u);
+        }
         if (lane == 0) {
           M.nent = -1;
           mbar_arrive(full_bar_w);
@@ -61,11 +69,11 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         break;
       }
       if (ra.t >= 0) {
-        if (!first) {
-          mbar_wait(empty_bar_w, parity);
-          parity ^= 1;
+        if (round >= 1) {
+          if (npp > 1) mbar_wait(turn_bar_w, (uint32_t)(round - 1) & 1u);
+          mbar_wait(empty_bar_w, (uint32_t)(round - 1) & 1u);
         }
-        first = false;
+        round += npp;
         const int nent = ra.nent;
         const int64_t o0 = ra.o0, o1 = ra.o1;
         const int64_t P0 = __shfl_sync(0xffffffffu, o0, 0);
@@ -154,7 +162,10 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           M.next = 0;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar_w);  // release: header + tail stores are visible
+        if (lane == 0) {
+          mbar_arrive(full_bar_w);  // release: header + tail stores are visible
+          if (npp > 1) mbar_arrive(turn_bar_w);
+        }
       }
       // ---------------- advance the pipeline: A <- B (+ level 3), B <- C (+ level 2), C <- D (+ level 1) ----
       ra = rb;
@@ -174,17 +185,6 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         }
       }
       rb = rc;
-      // The stages in shared memory cover ~1 us of DRAM latency only while all of them are in their
-      // copy phase; prefetching the point slice of a stage far ahead into L2 keeps DRAM busy
-      // independently of how long the compute phases hold the stage slots.
-      if (rb.t >= 0 && lane == 0 && rb.pf1 > rb.pf0) {
-        const int64_t a = rb.pf0 & ~(int64_t)1, b = rb.pf1 & ~(int64_t)1;
-        if (b > a) {
-          bulk_prefetch_l2(P.pts + a * DIM, (uint32_t)((b - a) * DIM * 8));
-          bulk_prefetch_l2(P.w + a, (uint32_t)((b - a) * 8));
-          if constexpr (T::NEED_NORMAL) bulk_prefetch_l2(P.normals + a * DIM, (uint32_t)((b - a) * DIM * 8));
-        }
-      }
       if (rb.t >= 0 && rb.valid) {
         const int32_t cell = rb.cell;
         if constexpr (DIM == 2) {
@@ -206,9 +206,8 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           for (int i = 0; i < NP16; ++i) rb.pos[i] = __ldg(src + i);
         }
       }
-      long long td = __shfl_sync(0xffffffffu, (long long)ticket, 0);
-      if (td >= num_stages) td = -1;
-      if (td >= 0 && lane == 0) ticket = atomicAdd(P.work_counter, 1u);
+      long long td = next_t < num_stages ? next_t : (next_t - round_t < num_stages ? -1 : -3);
+      next_t += step_t;
       rc.t = td;
       rc.valid = false;
       if (td >= 0) {
@@ -220,13 +219,6 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         rc.o0 = __ldg(P.offsets + k);
         rc.o1 = __ldg(P.offsets + k + 1);
         rc.cell = __ldg(P.cells + k);
-        rc.pf0 = rc.pf1 = 0;
-        const int64_t tp = td + P.prefetch_stages;
-        if (lane == 0 && P.prefetch_stages > 0 && tp < num_stages) {
-          const int64_t kp = tp * CB, kq = (kp + CB) < P.num_entries ? (kp + CB) : P.num_entries;
-          rc.pf0 = __ldg(P.offsets + kp);
-          rc.pf1 = __ldg(P.offsets + kq);
-        }
       }
     }
   }
@@ -264,7 +256,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
   double msum = 0.0;
 
   if (warp < NPW) {
-    staged_producer<T, G, CB>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages);
+    staged_producer<T, G, CB>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages, warp, NPW);
   } else {
     // =========================== consumer warps ===========================================
     const int r = lane & (G - 1), grp = lane / G;
@@ -317,8 +309,9 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
 // stage with one thread per entry.
 // ---------------------------------------------------------------------------------------------
 // XT: row-owned expansion with the transposed scatter (RowTile, cq_moment.cuh); NXW = sets * (DEG + 1)
-template <class T, int G, int NPW, int NMW, int NXW, bool XT = false>
-__global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
+// NPP: producer warps per stage slot
+template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1>
+__global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
   constexpr int CB = 32;
   using Meta = StageMeta<T, CB>;
   using Lay = StagedLayout<T, CB>;
@@ -327,7 +320,7 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
   static_assert(Meta::MOM, "moment kernel: 2-D mass / stiffness only");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t full_bar[NPW], mom_bar[NPW], empty_bar[NPW];
+  __shared__ uint64_t full_bar[NPW], mom_bar[NPW], empty_bar[NPW], turn_bar[NPW];
   const int PB = P.stage_points;
   const size_t stage_bytes = Lay::stage_bytes(PB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,6 +329,7 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
     for (int s = 0; s < NPW; ++s) {
       mbar_init(&full_bar[s], 2);
       mbar_init(&mom_bar[s], NMW);
+      mbar_init(&turn_bar[s], 1);
       mbar_init(&empty_bar[s], XT ? T::DEG + 1 : NXW);  // the expansion warps of one set
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -343,9 +337,11 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
   __syncthreads();
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
 
-  if (warp < NPW) {
-    staged_producer<T, G, CB>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages);
-  } else if (warp < NPW + NMW) {
+  if (warp < NPW * NPP) {
+    const int slot = warp % NPW, sub = warp / NPW;
+    staged_producer<T, G, CB>(P, smem_raw + (size_t)slot * stage_bytes, &full_bar[slot], &empty_bar[slot], lane, PB, num_stages, slot, NPW, sub,
+                              NPP, &turn_bar[slot]);
+  } else if (warp < NPW * NPP + NMW) {
     // ------------------------------ moment warps ------------------------------
     const int r = lane & (G - 1), grp = lane / G;
     uint32_t ended = 0, parity = 0;
@@ -383,7 +379,7 @@ __global__ void __launch_bounds__((NPW + NMW + NXW) * 32, 1) assemble_moment_spl
     constexpr int NROLE = XT ? T::DEG + 1 : NXW;
     constexpr int NXS = NXW / NROLE;
     static_assert(NXW % NROLE == 0 && NPW % NXS == 0, "expansion warps: whole sets, slots divisible by sets");
-    const int xw = warp - NPW - NMW;
+    const int xw = warp - NPW * NPP - NMW;
     const int role = xw % NROLE, set = xw / NROLE;
     uint32_t mine = 0;
 #pragma unroll
