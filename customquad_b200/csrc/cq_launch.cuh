@@ -112,8 +112,11 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NPW
 #define CQ_MOMENT_NPW 4
 #endif
-#ifndef CQ_MOMENT_NMW
+#ifndef CQ_MOMENT_NMW   // moment warps, degree 1 (4 + 8 + 2 = 14 warps)
 #define CQ_MOMENT_NMW 8
+#endif
+#ifndef CQ_MOMENT_NMW2  // moment warps, degree 2 (4 + 6 + 6 = 16 warps: 128 registers per thread, no spills)
+#define CQ_MOMENT_NMW2 6
 #endif
 #ifndef CQ_MOMENT_NXW1
 #define CQ_MOMENT_NXW1 3
@@ -144,7 +147,7 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // organisations are bound by the L2 atomic rate of the 81 REDs per cell (2.56 vs 2.59 ms)
         // split = 2: row-owned expansion + transposed scatter (RowTile, cq_moment.cuh)
         static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : 2;
-        if (split == 2) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1), true, CQ_MOMENT_NPP>(ctx, P, s);
+        if (split == 2) return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2), (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1), true, CQ_MOMENT_NPP>(ctx, P, s);
         if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1>(ctx, P, s);
         return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
       }

@@ -266,6 +266,9 @@ CQ_DEVINL void moment_expand_comp(const KParams& P, const StageMeta<T, CB>& M, c
 // create_rectangle is y-fastest) -> one sector per run of DEG+1 values (ncu: 2.5x fewer RED sectors,
 // 5x fewer L1 wavefronts).  The scatter loop is unrolled over the entries so that every address is
 // base + constant.
+#ifndef CQ_SCATTER_UNROLL
+#define CQ_SCATTER_UNROLL 4
+#endif
 template <int DEG>
 struct RowTile {
   static constexpr int D1 = DEG + 1, N = D1 * D1;
@@ -354,7 +357,8 @@ CQ_DEVINL void scatter_rows_transposed(const KParams& P, const StageMeta<T, CB>&
   double* const vals = P.values;
   if (P.bs == 1) {
     if (nent == CB) {
-#pragma unroll
+      constexpr int UNROLL = CQ_SCATTER_UNROLL;
+#pragma unroll UNROLL
       for (int e0 = 0; e0 < CB; e0 += EPI)
         red_add_f64(vals + rs[e0] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
     } else {

@@ -109,8 +109,23 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         M.pts[lane] = staged ? s_pts + (o0 - Pa) * DIM : P.pts + o0 * DIM;
         M.w[lane] = staged ? s_w + (o0 - Pa) : P.w + o0;
         if constexpr (T::NEED_NORMAL) M.nrm[lane] = staged ? s_nrm + (o0 - Pa) * DIM : P.normals + o0 * DIM;
+        if constexpr (POS_BULK) {
+          // consecutive cells (the usual case): the 32 map rows are one contiguous slice -> one bulk copy.
+          // Keep this at warp-uniform control flow: nesting the per-lane copy loop (UBLKCP is issued
+          // through uniform registers, one lane at a time) under a second divergent branch hung the warp.
+#ifndef CQ_NO_POS_FASTPATH
+          const int cell0 = __shfl_sync(0xffffffffu, ra.cell, 0);
+          const bool consec = __all_sync(0xffffffffu, ra.valid && ra.cell == cell0 + lane);
+#else
+          const bool consec = false;
+#endif
+          if (consec) {
+            if (lane == 0) bulk_g2s(&M.pos[0][0], P.elem_pos + (int64_t)cell0 * Meta::NPOS, CB * Meta::NPOS, full_bar_w);
+          } else if (ra.valid) {
+            bulk_g2s(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, full_bar_w);
+          }
+        }
         if (ra.valid) {
-          if constexpr (POS_BULK) bulk_g2s(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, full_bar_w);
           if constexpr (Meta::MAT) {
             if constexpr (!POS_BULK) {
               int4* dst = reinterpret_cast<int4*>(&M.pos[lane][0]);
