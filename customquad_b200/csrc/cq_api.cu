@@ -128,6 +128,29 @@ __global__ void scatter_map_kernel(const int32_t* __restrict__ dofmap, int64_t n
   }
 }
 
+// rowmin[c] = min over the entries k in chunk c of the smallest (blocked) row cell cells[k] touches
+__global__ void chunk_rowmin_kernel(const int32_t* __restrict__ cells, int64_t num_entries, int nchunks, const int32_t* __restrict__ dofmap,
+                                    int n, int bs, int32_t* __restrict__ rowmin) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < num_entries; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c0 = cells[k];
+    int32_t m = 0x7fffffff;
+    for (int i = 0; i < n; ++i) m = min(m, dofmap[c0 * n + i]);
+    // chunk of entry k: chunks are [C*c/nchunks, C*(c+1)/nchunks)
+    int c = (int)((k * nchunks) / num_entries);
+    while (c + 1 < nchunks && k >= num_entries * (c + 1) / nchunks) ++c;
+    while (c > 0 && k < num_entries * c / nchunks) --c;
+    m = __reduce_min_sync(__activemask(), m);  // same chunk for (almost) the whole warp: one atomic per warp in the common case
+    const int cw = __shfl_sync(__activemask(), c, __ffs(__activemask()) - 1);
+    if (__all_sync(__activemask(), c == cw)) {
+      if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicMin(rowmin + c, m * bs);
+    } else {
+      int32_t mine = 0x7fffffff;
+      for (int i = 0; i < n; ++i) mine = min(mine, dofmap[c0 * n + i]);
+      atomicMin(rowmin + c, mine * bs);
+    }
+  }
+}
+
 // call_basix on the device: one thread per (point, dof)
 template <int DIM, int DEG>
 __global__ void tabulate_kernel(const double* __restrict__ pts, int64_t nq, int deriv, double* __restrict__ out) {
@@ -177,7 +200,12 @@ int cq_ctx_create(int device, cq_ctx** out) {
   if (!rc) rc = check_cuda(cudaMalloc(&c->work_counter, sizeof(unsigned int)), "cudaMalloc(work_counter)");
   if (!rc) rc = check_cuda(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), "cudaDeviceGetAttribute");
   if (!rc) rc = check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  for (int i = 0; i < 8 && !rc; ++i) rc = check_cuda(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming), "cudaEventCreate");
+  if (!rc) rc = check_cuda(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (int i = 0; i < 12 && !rc; ++i) rc = check_cuda(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming), "cudaEventCreate");
+  for (int i = 0; i < 16 && !rc; ++i) rc = check_cuda(cudaEventCreateWithFlags(&c->kev[i], cudaEventDisableTiming), "cudaEventCreate");
+  if (!rc) rc = check_cuda(cudaMalloc(&c->chunk_rowmin, 16 * sizeof(int32_t)), "cudaMalloc(chunk_rowmin)");
+  if (!rc) rc = check_cuda(cudaHostAlloc(&c->host_rowmin, 16 * sizeof(int32_t), cudaHostAllocDefault), "cudaHostAlloc");
+  if (!rc) rc = check_cuda(cudaHostAlloc(&c->host_vallo, 16 * sizeof(int64_t), cudaHostAllocDefault), "cudaHostAlloc");
   if (!rc) rc = check_cuda(cudaHostAlloc(&c->host_flag, sizeof(int), cudaHostAllocDefault), "cudaHostAlloc");
   if (rc) { cq_ctx_destroy(c); return rc; }
   *out = c;
@@ -193,7 +221,12 @@ int cq_ctx_destroy(cq_ctx* ctx) {
   if (ctx->scalar_dev) cudaFree(ctx->scalar_dev);
   if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  if (ctx->chunk_rowmin) cudaFree(ctx->chunk_rowmin);
+  if (ctx->host_rowmin) cudaFreeHost(ctx->host_rowmin);
+  if (ctx->host_vallo) cudaFreeHost(ctx->host_vallo);
   delete ctx;
   return CQ_OK;
 }
@@ -397,8 +430,12 @@ static int ensure_stage(cq_ctx* ctx, size_t bytes) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-template <class LaunchFn>
-static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_quadrature* qh, cudaStream_t s, LaunchFn&& launch) {
+static int no_after_chunk(int, int, const int64_t*) { return CQ_OK; }
+
+// rows_back: also work out val_lo[c] (see cq_assemble_matrix_host) before the first chunk is launched
+template <class LaunchFn, class AfterFn>
+static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* /*mesh*/, const cq_space* space, const cq_csr* A,
+                            const cq_quadrature* qh, cudaStream_t s, bool rows_back, LaunchFn&& launch, AfterFn&& after) {
   if (!ctx || !form || !qh) { set_error("null argument"); return CQ_ERR_INVALID; }
   const int gdim = gdim_of(form->cell_type);
   const int64_t C = qh->num_entries, Pn = qh->num_points;
@@ -422,10 +459,39 @@ static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_quad
   qd.normals = qh->normals ? reinterpret_cast<double*>(base + o_n) : nullptr;
 
   // copy stream must not start before prior work on `s` that may still read the staging buffer
-  if (int rc = check_cuda(cudaEventRecord(ctx->ev[7], s), "cudaEventRecord")) return rc;
-  if (int rc = check_cuda(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[7], 0), "cudaStreamWaitEvent")) return rc;
+  if (int rc = check_cuda(cudaEventRecord(ctx->ev[11], s), "cudaEventRecord")) return rc;
+  if (int rc = check_cuda(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[11], 0), "cudaStreamWaitEvent")) return rc;
 
-  const int nchunks = C >= (1 << 16) ? 6 : 1;
+  const int nchunks = C >= (1 << 16) ? 8 : 1;
+  int64_t val_lo[17];
+  for (int c = 0; c <= nchunks; ++c) val_lo[c] = 0;
+  if (rows_back && nchunks > 1 && space && space->dofmap && A && A->indptr) {
+    // all cell ids first (small), then the per-chunk smallest row and its CSR offset
+    cudaStream_t cs = ctx->copy_stream;
+    int rc = check_cuda(cudaMemcpyAsync(const_cast<int32_t*>(qd.cells), qh->cells, sizeof(int32_t) * C, cudaMemcpyHostToDevice, cs), "H2D cells");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(ctx->chunk_rowmin, 0x7f, 16 * sizeof(int32_t), cs), "rowmin init");
+    if (rc) return rc;
+    int n = form->degree + 1;
+    n = gdim == 2 ? n * n : n * n * n;
+    chunk_rowmin_kernel<<<ctx->num_sms * 4, 256, 0, cs>>>(qd.cells, C, nchunks, space->dofmap, n, form->bs, ctx->chunk_rowmin);
+    ctx->launches++;
+    rc = check_cuda(cudaGetLastError(), "chunk_rowmin_kernel launch");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(ctx->host_rowmin, ctx->chunk_rowmin, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, cs), "rowmin D2H");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
+    if (rc) return rc;
+    int32_t suffix = 0x7fffffff;
+    for (int c = nchunks - 1; c >= 0; --c) {
+      if (ctx->host_rowmin[c] < suffix) suffix = ctx->host_rowmin[c];
+      ctx->host_rowmin[c] = suffix;
+    }
+    for (int c = 0; c < nchunks && !rc; ++c) {
+      const int64_t row = ctx->host_rowmin[c] < A->num_rows ? ctx->host_rowmin[c] : A->num_rows;
+      rc = check_cuda(cudaMemcpyAsync(ctx->host_vallo + c, A->indptr + row, sizeof(int64_t), cudaMemcpyDeviceToHost, cs), "indptr D2H");
+    }
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
+    if (rc) return rc;
+    for (int c = 0; c < nchunks; ++c) val_lo[c] = ctx->host_vallo[c];
+  }
   for (int c = 0; c < nchunks; ++c) {
     const int64_t k0 = C * c / nchunks, k1 = C * (c + 1) / nchunks;
     if (k1 == k0) continue;
@@ -447,6 +513,7 @@ static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_quad
     qc.offsets = qd.offsets + k0;
     qc.num_entries = k1 - k0;
     if (int lrc = launch(qc)) return lrc;
+    if (int arc = after(c, nchunks, val_lo)) return arc;
   }
   return CQ_OK;
 }
@@ -459,11 +526,28 @@ int cq_assemble_matrix_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctx) cudaSetDevice(ctx->device);
   if (int rc = check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * A->nnz, s), "zeroEntries")) return rc;  // A.zeroEntries()
-  int rc = run_host_chunked(ctx, form, qr_host, s, [&](const cq_quadrature& qc) { return cq_assemble_matrix(ctx, form, mesh, space, &qc, A, stream); });
+  // Rows are final once no later chunk touches them: values below val_lo[c + 1] (the CSR offset of the smallest row
+  // any chunk after c touches) go back to the host on a second stream while the points of the later chunks are still
+  // coming in (PCIe is full duplex).  For a sorted cell list with a locality-preserving dof numbering that hides all
+  // but the last chunk's rows; for an arbitrary list val_lo is 0 and everything is copied at the end, as before.
+  int64_t copied = 0;
+  auto after_chunk = [&](int c, int nchunks, const int64_t* val_lo) -> int {
+    if (!values_host || c + 1 >= nchunks) return CQ_OK;
+    const int64_t upto = val_lo[c + 1];
+    if (upto <= copied) return CQ_OK;
+    int rc = check_cuda(cudaEventRecord(ctx->kev[c], s), "cudaEventRecord");
+    if (!rc) rc = check_cuda(cudaStreamWaitEvent(ctx->d2h_stream, ctx->kev[c], 0), "cudaStreamWaitEvent");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(values_host + copied, A->values + copied, sizeof(double) * (upto - copied), cudaMemcpyDeviceToHost, ctx->d2h_stream), "D2H rows");
+    copied = upto;
+    return rc;
+  };
+  int rc = run_host_chunked(ctx, form, mesh, space, A, qr_host, s, values_host != nullptr,
+                            [&](const cq_quadrature& qc) { return cq_assemble_matrix(ctx, form, mesh, space, &qc, A, stream); }, after_chunk);
   if (rc) return rc;
-  if (values_host)
-    if (int rc2 = check_cuda(cudaMemcpyAsync(values_host, A->values, sizeof(double) * A->nnz, cudaMemcpyDeviceToHost, s), "D2H values")) return rc2;
-  return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  if (values_host && A->nnz > copied)
+    if (int rc2 = check_cuda(cudaMemcpyAsync(values_host + copied, A->values + copied, sizeof(double) * (A->nnz - copied), cudaMemcpyDeviceToHost, s), "D2H values")) return rc2;
+  if (int rc2 = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc2;
+  return check_cuda(cudaStreamSynchronize(ctx->d2h_stream), "cudaStreamSynchronize(d2h)");
 }
 
 int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
@@ -473,7 +557,8 @@ int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
   if (ctx) cudaSetDevice(ctx->device);
   const size_t bytes = sizeof(double) * space->num_dofs * (form ? form->bs : 1);
   if (int rc = check_cuda(cudaMemsetAsync(b_dev, 0, bytes, s), "zero b")) return rc;
-  int rc = run_host_chunked(ctx, form, qr_host, s, [&](const cq_quadrature& qc) { return cq_assemble_vector(ctx, form, mesh, space, &qc, b_dev, stream); });
+  int rc = run_host_chunked(ctx, form, mesh, space, nullptr, qr_host, s, false,
+                            [&](const cq_quadrature& qc) { return cq_assemble_vector(ctx, form, mesh, space, &qc, b_dev, stream); }, no_after_chunk);
   if (rc) return rc;
   if (b_host)
     if (int rc2 = check_cuda(cudaMemcpyAsync(b_host, b_dev, bytes, cudaMemcpyDeviceToHost, s), "D2H b")) return rc2;
@@ -489,7 +574,8 @@ int cq_assemble_scalar_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
     if (int rc = check_cuda(cudaMalloc(&ctx->scalar_dev, sizeof(double)), "cudaMalloc(m)")) return rc;
   double* m_dev = ctx->scalar_dev;
   if (int rc = check_cuda(cudaMemsetAsync(m_dev, 0, sizeof(double), s), "zero m")) return rc;
-  int rc = run_host_chunked(ctx, form, qr_host, s, [&](const cq_quadrature& qc) { return cq_assemble_scalar(ctx, form, mesh, space, &qc, m_dev, stream); });
+  int rc = run_host_chunked(ctx, form, mesh, space, nullptr, qr_host, s, false,
+                            [&](const cq_quadrature& qc) { return cq_assemble_scalar(ctx, form, mesh, space, &qc, m_dev, stream); }, no_after_chunk);
   if (rc) return rc;
   if (int rc2 = check_cuda(cudaMemcpyAsync(m_host, m_dev, sizeof(double), cudaMemcpyDeviceToHost, s), "D2H m")) return rc2;
   return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");

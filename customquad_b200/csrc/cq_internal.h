@@ -18,7 +18,12 @@ struct cq_ctx {
   std::atomic<int64_t> launches{0};
   // end-to-end (host buffer) path: grow-only device staging + a copy stream
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaStream_t d2h_stream = nullptr;  // result rows go back while later chunks are still coming in
+  cudaEvent_t ev[12] = {};
+  cudaEvent_t kev[16] = {};           // "kernel of chunk c done"
+  int32_t* chunk_rowmin = nullptr;    // device [16]
+  int32_t* host_rowmin = nullptr;     // pinned [16]
+  int64_t* host_vallo = nullptr;      // pinned [16]
   void* stage = nullptr;
   size_t stage_bytes = 0;
   int* host_flag = nullptr;  // pinned

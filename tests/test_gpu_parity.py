@@ -305,6 +305,17 @@ def test_host_buffer_entry_points(cuda_backend, oracle_backend):
     asm.assemble_matrix_host(form, qr, A, vals)
     R = oracle_backend.matrix(form, [qr])
     assert close(vals, R.data)
+    # rows go back to the host as soon as no later chunk touches them: reversed and shuffled cell
+    # orders (nothing / little is final early) and a degree-2 space must give the same values
+    rng = np.random.default_rng(8)
+    V2 = cq.FunctionSpace(mesh, ("Lagrange", 2))
+    for cells, space in ((np.arange(mesh.num_cells)[::-1].copy(), V), (rng.permutation(mesh.num_cells), V), (np.arange(mesh.num_cells), V2)):
+        q2 = synthetic_ragged(cells, 2, 1, 6, seed=5)
+        f2 = forms.mass(space)
+        A2 = asm.create_matrix(f2)
+        v2 = np.full(A2.nnz, np.nan)
+        asm.assemble_matrix_host(f2, q2, A2, v2)
+        assert close(v2, oracle_backend.matrix(f2, [q2]).data)
     b = cq.la.Vector(torch.zeros(V.num_dofs, dtype=torch.float64, device="cuda"), 0)
     bh = np.zeros(V.num_dofs)
     lf = forms.load(V, cq.Analytic.sinprod(2 * np.pi**2))
