@@ -78,7 +78,7 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   if (pb < 64) pb = 64;
   if constexpr (XT) {
     // the expansion tiles of a stage reuse its point buffer: it has to hold (DEG + 1) of them
-    const int64_t need = (int64_t)(((T::DEG + 1) * RowTile<T::DEG>::bytes(CB) + T::DIM * 8 - 1) / (T::DIM * 8));
+    const int64_t need = (int64_t)(((T::DEG + 1) * RowTile<T::DIM, T::DEG>::bytes(CB) + T::DIM * 8 - 1) / (T::DIM * 8));
     if (pb < need) pb = (need + 1) & ~(int64_t)1;
     if (pb > pb_max) { set_error("moment kernel: expansion tiles do not fit the stage"); return CQ_ERR_UNSUPPORTED; }
   }
@@ -124,6 +124,15 @@ struct StagedShape {
 #ifndef CQ_MOMENT_SG
 #define CQ_MOMENT_SG 4
 #endif
+#ifndef CQ_MOMENT_G3    // Q1 hexahedra: lanes per entry in the point loop, moment warps, expansion warp sets
+#define CQ_MOMENT_G3 2
+#endif
+#ifndef CQ_MOMENT_NMW3
+#define CQ_MOMENT_NMW3 6
+#endif
+#ifndef CQ_MOMENT_NXS3
+#define CQ_MOMENT_NXS3 2
+#endif
 #ifndef CQ_MOMENT_NPP  // producer warps per stage slot
 #define CQ_MOMENT_NPP 1
 #endif
@@ -151,6 +160,11 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1>(ctx, P, s);
         return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
       }
+    }
+    // ... and on Q1 hexahedra (create_box meshes): 27 moments, two expansion roles
+    if constexpr (T::DIM == 3 && T::DEG == 1 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {
+      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3)
+        return launch_moment_split<T, CQ_MOMENT_G3, 4, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
     }
     return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
   }

@@ -169,15 +169,52 @@ CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const b
 
 // Split kernels: the moments of an entry go to the stage header, so instead of an all-reduce the
 // G lanes transpose-reduce (M (1 - 1/G) shuffles) and lane r stores its slice of the sums.
+// Q1 hexahedron: mu[(p * 3 + q) * 3 + r] = sum w t0^p t1^q t2^r, p, q, r <= 2 (39 FP64 instructions per point)
+template <class T, int G, int CB, int MPAD>
+CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const bool active, const int r, double (&acc)[MPAD]) {
+  constexpr int Pn = 3;
+#pragma unroll
+  for (int k = 0; k < MPAD; ++k) acc[k] = 0.0;
+  const int nq = active ? M.nq[e] : 0;
+  const double* pp = M.pts[e];
+  const double* wp = M.w[e];
+#pragma unroll 2
+  for (int q = r; q < nq; q += G) {
+    const double t0 = pp[3 * q] - 0.5, t1 = pp[3 * q + 1] - 0.5, t2 = pp[3 * q + 2] - 0.5;
+    const double w = wp[q];
+    double Z[Pn], YZ[Pn][Pn];
+    Z[0] = w; Z[1] = w * t2; Z[2] = Z[1] * t2;
+    const double t11 = t1 * t1, t00 = t0 * t0;
+#pragma unroll
+    for (int c = 0; c < Pn; ++c) {
+      YZ[0][c] = Z[c];
+      YZ[1][c] = t1 * Z[c];
+      YZ[2][c] = t11 * Z[c];
+    }
+#pragma unroll
+    for (int b = 0; b < Pn; ++b)
+#pragma unroll
+      for (int c = 0; c < Pn; ++c) {
+        acc[(0 * Pn + b) * Pn + c] += YZ[b][c];
+        acc[(1 * Pn + b) * Pn + c] = fma(t0, YZ[b][c], acc[(1 * Pn + b) * Pn + c]);
+        acc[(2 * Pn + b) * Pn + c] = fma(t00, YZ[b][c], acc[(2 * Pn + b) * Pn + c]);
+      }
+  }
+}
+
 template <class T, int G, int CB>
 CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const bool active, const bool compute, const int r) {
-  constexpr int Pn = 2 * T::DEG + 1, NM = Pn * Pn;
+  constexpr int Pn = 2 * T::DEG + 1, NM = StageMeta<T, CB>::NMOM;
   constexpr int MPAD = round_up(NM, G), B = MPAD / G;
-  double mu[Pn][Pn];
-  moment_accumulate<T, G, CB, false>(M, e, active && compute, r, mu);
   double acc[MPAD];
+  if constexpr (T::DIM == 3) {
+    moment_accumulate3<T, G, CB, MPAD>(M, e, active && compute, r, acc);
+  } else {
+    double mu[Pn][Pn];
+    moment_accumulate<T, G, CB, false>(M, e, active && compute, r, mu);
 #pragma unroll
-  for (int k = 0; k < MPAD; ++k) acc[k] = k < NM ? mu[k / Pn][k % Pn] : 0.0;
+    for (int k = 0; k < MPAD; ++k) acc[k] = k < NM ? mu[k / Pn][k % Pn] : 0.0;
+  }
   transpose_reduce_step<MPAD, G / 2>(acc, r);
   if (active) {
 #pragma unroll
@@ -269,25 +306,124 @@ CQ_DEVINL void moment_expand_comp(const KParams& P, const StageMeta<T, CB>& M, c
 #ifndef CQ_SCATTER_UNROLL
 #define CQ_SCATTER_UNROLL 4
 #endif
-template <int DEG>
+template <int DIM, int DEG>
 struct RowTile {
-  static constexpr int D1 = DEG + 1, N = D1 * D1;
-  static constexpr int NVW = D1 * N;        // values per entry owned by one expansion warp
+  static constexpr int D1 = DEG + 1, N = DIM == 2 ? D1 * D1 : D1 * D1 * D1;
+  static constexpr int NROLE = D1;          // expansion roles: the x lattice index A0 of the owned rows
+  static constexpr int NVW = (N / D1) * N;  // values per entry owned by one expansion warp (Q1 quad 8, Q2 quad 27, Q1 hex 32)
   static constexpr int STRIDE = NVW | 1;    // odd stride: conflict-free one-thread-per-entry writes
-  static constexpr int EPI = 32 / NVW;      // entries per scatter instruction (Q1: 4, Q2: 1)
+  static constexpr int EPI = 32 / NVW;      // entries per scatter instruction (Q1 quad: 4, Q2 quad / Q1 hex: 1)
   static constexpr size_t bytes(int cb) { return (size_t)cb * STRIDE * 8; }
-  // local dof of lattice point (x, y), 4 bits each, index x * D1 + y
+  // quadrilaterals: local dof of lattice point (x, y), 4 bits each, index x * D1 + y
   CQ_HD static constexpr uint64_t dof_table() {
     uint64_t t = 0;
-    for (int x = 0; x < D1; ++x)
-      for (int y = 0; y < D1; ++y) t |= (uint64_t)quad_dof_of<DEG>(x, y) << (4 * (x * D1 + y));
+    if (DIM == 2)
+      for (int x = 0; x < D1; ++x)
+        for (int y = 0; y < D1; ++y) t |= (uint64_t)quad_dof_of<DEG>(x, y) << (4 * (x * D1 + y));
     return t;
   }
 };
 
 // lane = entry e: values (a1, c0, c1) of the rows with x index A0 -> tile[(a1 * D1 + c0) * D1 + c1]
+// Q1 hexahedron (local dof j = a0 + 2 a1 + 4 a2, Lattice<3,1>): rows i = A0 + 2 (a1 + 2 a2), all 8 columns
+// j = c0 + 2 c1 + 4 c2 -> tile[(a1 + 2 a2) * 8 + j].  The three indices are contracted one after the other
+// (x, y, z); stiffness carries the three derivative placements (R11 in x | y | z) through the chain.
+template <class T, int CB, int A0>
+CQ_DEVINL void moment_expand_rows3(const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
+  static_assert(T::DIM == 3 && T::DEG == 1, "Q1 hexahedron");
+  using Q = Poly1D<1>;
+  constexpr int Pn = 3;
+  constexpr bool STIFF = T::FORM_ID == CQ_FORM_STIFFNESS;
+  double mu[Pn][Pn][Pn];
+#pragma unroll
+  for (int p = 0; p < Pn; ++p)
+#pragma unroll
+    for (int q = 0; q < Pn; ++q)
+#pragma unroll
+      for (int r = 0; r < Pn; ++r) mu[p][q][r] = M.mu[(p * Pn + q) * Pn + r][e];
+  const double kM = M.kc[0][e];
+  const double kx = STIFF ? M.kc[1][e] : 0.0, ky = STIFF ? M.kc[2][e] : 0.0, kz = STIFF ? M.kc[3][e] : 0.0;
+  static_for<0, 2>([&](auto C0) {
+    constexpr int c0 = decltype(C0)::value;
+    // x: U0 = R00x . mu, U1 = R11x . mu
+    double U0[Pn][Pn], U1[Pn][Pn];
+    bool i0 = false, i1 = false;
+    static_for<0, Pn>([&](auto PP) {
+      constexpr int p = decltype(PP)::value;
+      constexpr double r00 = Q::R00(A0, c0, p), r11 = Q::R11(A0, c0, p);
+      if constexpr (r00 != 0.0) {
+#pragma unroll
+        for (int q = 0; q < Pn; ++q)
+#pragma unroll
+          for (int r = 0; r < Pn; ++r) U0[q][r] = i0 ? fma(r00, mu[p][q][r], U0[q][r]) : r00 * mu[p][q][r];
+        i0 = true;
+      }
+      if constexpr (STIFF && r11 != 0.0) {
+#pragma unroll
+        for (int q = 0; q < Pn; ++q)
+#pragma unroll
+          for (int r = 0; r < Pn; ++r) U1[q][r] = i1 ? fma(r11, mu[p][q][r], U1[q][r]) : r11 * mu[p][q][r];
+        i1 = true;
+      }
+    });
+    static_for<0, 2>([&](auto A1) {
+      static_for<0, 2>([&](auto C1) {
+        constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
+        // y: V00 = R00y . U0 (mass, d/dz d/dz), V01 = R11y . U0 (d/dy d/dy), V10 = R00y . U1 (d/dx d/dx)
+        double V00[Pn], V01[Pn], V10[Pn];
+        bool j00 = false, j01 = false, j10 = false;
+        static_for<0, Pn>([&](auto QQ) {
+          constexpr int q = decltype(QQ)::value;
+          constexpr double r00 = Q::R00(a1, c1, q), r11 = Q::R11(a1, c1, q);
+          if constexpr (r00 != 0.0) {
+#pragma unroll
+            for (int r = 0; r < Pn; ++r) V00[r] = j00 ? fma(r00, U0[q][r], V00[r]) : r00 * U0[q][r];
+            j00 = true;
+            if constexpr (STIFF) {
+#pragma unroll
+              for (int r = 0; r < Pn; ++r) V10[r] = j10 ? fma(r00, U1[q][r], V10[r]) : r00 * U1[q][r];
+              j10 = true;
+            }
+          }
+          if constexpr (STIFF && r11 != 0.0) {
+#pragma unroll
+            for (int r = 0; r < Pn; ++r) V01[r] = j01 ? fma(r11, U0[q][r], V01[r]) : r11 * U0[q][r];
+            j01 = true;
+          }
+        });
+        static_for<0, 2>([&](auto A2) {
+          static_for<0, 2>([&](auto C2) {
+            constexpr int a2 = decltype(A2)::value, c2 = decltype(C2)::value;
+            double m = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+            bool km = false, ks = false, kzz = false;
+            static_for<0, Pn>([&](auto RR) {
+              constexpr int r = decltype(RR)::value;
+              constexpr double r00 = Q::R00(a2, c2, r), r11 = Q::R11(a2, c2, r);
+              if constexpr (!STIFF) {
+                if constexpr (r00 != 0.0) { m = km ? fma(r00, V00[r], m) : r00 * V00[r]; km = true; }
+              } else {
+                if constexpr (r00 != 0.0) {
+                  sx = ks ? fma(r00, V10[r], sx) : r00 * V10[r];
+                  sy = ks ? fma(r00, V01[r], sy) : r00 * V01[r];
+                  ks = true;
+                }
+                if constexpr (r11 != 0.0) { sz = kzz ? fma(r11, V00[r], sz) : r11 * V00[r]; kzz = true; }
+              }
+            });
+            tile[(a1 + 2 * a2) * 8 + (c0 + 2 * c1 + 4 * c2)] = STIFF ? fma(kx, sx, fma(ky, sy, kz * sz)) : kM * m;
+          });
+        });
+      });
+    });
+  });
+}
+
 template <class T, int CB, int A0>
 CQ_DEVINL void moment_expand_rows(const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
+  if constexpr (T::DIM == 3) {
+    moment_expand_rows3<T, CB, A0>(M, e, tile);
+    return;
+  } else {
   constexpr int DEG = T::DEG, D1 = DEG + 1;
   using Q = Poly1D<DEG>;
   constexpr int Pn = Q::P;
@@ -337,6 +473,7 @@ CQ_DEVINL void moment_expand_rows(const StageMeta<T, CB>& M, const int e, double
       });
     });
   });
+  }
 }
 
 // All 32 lanes.  tile: nent entries of RowTile::NVW values at stride RowTile::STRIDE.  Lane ->
@@ -344,13 +481,20 @@ CQ_DEVINL void moment_expand_rows(const StageMeta<T, CB>& M, const int e, double
 template <class T, int CB, int A0>
 CQ_DEVINL void scatter_rows_transposed(const KParams& P, const StageMeta<T, CB>& M, const double* __restrict__ tile, const int nent,
                                        const int lane) {
-  using RT = RowTile<T::DEG>;
+  using RT = RowTile<T::DIM, T::DEG>;
   constexpr int D1 = RT::D1, N = RT::N, NVW = RT::NVW, EPI = RT::EPI;
   constexpr uint64_t TBL = RT::dof_table();
   const int sub = lane / NVW, s = lane - sub * NVW;
   if (sub >= EPI) return;
-  const int a1 = s / N, cc = s - a1 * N;  // cc = c0 * D1 + c1
-  const int i = (int)((TBL >> (4 * (A0 * D1 + a1))) & 15u), j = (int)((TBL >> (4 * cc)) & 15u);
+  int i, j;
+  if constexpr (T::DIM == 2) {
+    const int a1 = s / N, cc = s - a1 * N;  // cc = c0 * D1 + c1
+    i = (int)((TBL >> (4 * (A0 * D1 + a1))) & 15u);
+    j = (int)((TBL >> (4 * cc)) & 15u);
+  } else {  // Q1 hexahedron: s = (a1 + 2 a2) * 8 + j
+    i = A0 + 2 * (s >> 3);
+    j = s & 7;
+  }
   const double* tl = tile + sub * RT::STRIDE + s;
   const uint8_t* pp = &M.pos[sub][i * N + j];
   const long long* rs = &M.rowstart[i][sub];

@@ -79,10 +79,13 @@ struct StageMeta {
   alignas(16) uint8_t pos[MAT ? CB : 1][MAT ? NPOS : 16];
   double coef[T::NEED_COEF ? T::NCOEF : 1][CB];
   // monomial moments handed from the moment warps to the expansion warps (cq_moment.cuh, split kernel)
-  static constexpr bool MOM = T::DIM == 2 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS);
-  static constexpr int NMOM = MOM ? (2 * T::DEG + 1) * (2 * T::DEG + 1) : 1;
+  // (quadrilaterals of degree 1 and 2, hexahedra of degree 1)
+  static constexpr bool MOMF = T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS;
+  static constexpr bool MOM = MOMF && (T::DIM == 2 || (T::DIM == 3 && T::DEG == 1));
+  static constexpr int PN = 2 * T::DEG + 1;
+  static constexpr int NMOM = MOM ? (T::DIM == 2 ? PN * PN : PN * PN * PN) : 1;
   double mu[NMOM][CB];
-  double kc[MOM ? 3 : 1][CB];  // axis-aligned cell constants: |det J|, |det J|/J00^2, |det J|/J11^2 (producer)
+  double kc[MOM ? 4 : 1][CB];  // axis-aligned cell constants: |det J|, |det J|/J_dd^2 for d = 0..DIM-1 (producer)
 };
 
 template <class T, int CB>

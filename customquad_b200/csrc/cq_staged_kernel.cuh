@@ -140,13 +140,24 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           }
 #pragma unroll
           for (int i = 0; i < NV * DIM; ++i) M.X[i][lane] = ra.X[i];
-          if constexpr (Meta::MOM) {
+          if constexpr (Meta::MOM && DIM == 2) {
             // J = diag(J00, J11): local vertex 2 is the +x neighbour, local vertex 1 the +y neighbour (Lattice<2,1>)
             const double J00 = ra.X[2 * 2 + 0] - ra.X[0], J11 = ra.X[1 * 2 + 1] - ra.X[1];
             M.kc[0][lane] = fabs(J00 * J11);
             if constexpr (T::FORM_ID == CQ_FORM_STIFFNESS) {
               M.kc[1][lane] = fabs(J11 / J00);
               M.kc[2][lane] = fabs(J00 / J11);
+            }
+          }
+          if constexpr (Meta::MOM && DIM == 3) {
+            // hexahedron: local vertex 1 / 2 / 4 is the +x / +y / +z neighbour (Lattice<3,1>)
+            const double J00 = ra.X[1 * 3 + 0] - ra.X[0], J11 = ra.X[2 * 3 + 1] - ra.X[1], J22 = ra.X[4 * 3 + 2] - ra.X[2];
+            const double adet = fabs(J00 * J11 * J22);
+            M.kc[0][lane] = adet;
+            if constexpr (T::FORM_ID == CQ_FORM_STIFFNESS) {
+              M.kc[1][lane] = adet / (J00 * J00);
+              M.kc[2][lane] = adet / (J11 * J11);
+              M.kc[3][lane] = adet / (J22 * J22);
             }
           }
           if constexpr (Meta::VEC) {
@@ -332,7 +343,8 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
   using Lay = StagedLayout<T, CB>;
   constexpr int CPW = 32 / G;
   constexpr int Pn = 2 * T::DEG + 1;
-  static_assert(Meta::MOM, "moment kernel: 2-D mass / stiffness only");
+  static_assert(Meta::MOM, "moment kernel: mass / stiffness on quadrilaterals (degree 1, 2) and hexahedra (degree 1)");
+  static_assert(XT || T::DIM == 2, "hexahedra: row-owned expansion only");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NPW], mom_bar[NPW], empty_bar[NPW], turn_bar[NPW];
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
         } else {
           if constexpr (XT) {
             // this warp's tile lives in the stage's point buffer (dead after the moment phase)
-            using RT = RowTile<T::DEG>;
+            using RT = RowTile<T::DIM, T::DEG>;
             double* tile = reinterpret_cast<double*>(smem_raw + (size_t)s * stage_bytes + Lay::meta_bytes + (size_t)role * RT::bytes(CB));
             if (P.dbg != 2) {
               static_for<0, T::DEG + 1>([&](auto RR) {
@@ -423,7 +435,8 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
                 }
               });
             }
-          } else if (lane < nent && P.dbg != 2) {
+          } else if constexpr (T::DIM == 2) {
+           if (lane < nent && P.dbg != 2) {
             double mu[Pn][Pn];
 #pragma unroll
             for (int p = 0; p < Pn; ++p)
@@ -432,6 +445,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
             static_for<0, NXW>([&](auto XW) {
               if (xw == decltype(XW)::value) moment_expand<T, 1, CB, decltype(XW)::value, NXW>(P, M, lane, 0, mu);
             });
+           }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty_bar[s]);

@@ -205,6 +205,29 @@ def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
     assert mesh_on_device(dist, torch.device("cuda", torch.cuda.current_device()))[2] == 0
 
 
+@pytest.mark.parametrize("bs", [1, 3])
+def test_moment_kernel_hexahedra(cuda_backend, oracle_backend, bs):
+    """Axis-aligned Q1 hexahedra (create_box) take the 27-moment kernel for mass / stiffness."""
+    from customquad_b200.assemble import mesh_on_device, set_variant
+    import torch
+
+    mesh = cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [7, 5, 6])
+    assert mesh_on_device(mesh, torch.device("cuda", torch.cuda.current_device()))[2] == 1  # CQ_MESH_AXIS_ALIGNED
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", 1))
+    rng = np.random.default_rng(37)
+    cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 40), np.arange(mesh.num_cells)])
+    qr = synthetic_ragged(cells, 3, 0, 40, seed=17)
+    for form in (forms.mass(V), forms.stiffness(V)):
+        R = oracle_backend.matrix(form, [qr])
+        set_variant(0)
+        A = cuda_backend.matrix(form, [qr])
+        set_variant(3)  # same staged kernel family without moments
+        B = cuda_backend.matrix(form, [qr])
+        set_variant(0)
+        assert close(A.data, R.data), f"{form.kind.name}: {np.max(np.abs(A.data - R.data)) / np.max(np.abs(R.data)):.3e}"
+        assert close(B.data, R.data)
+
+
 def test_staged_kernel_stage_overflow_and_tails(cuda_backend, oracle_backend):
     """Staged kernel corner cases: a rule far longer than a shared-memory stage (read from global
     memory), an odd total point count (manual tail copy), many stages, zero-point entries."""
