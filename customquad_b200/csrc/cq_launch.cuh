@@ -128,7 +128,7 @@ struct StagedShape {
 #define CQ_MOMENT_G3 2
 #endif
 #ifndef CQ_MOMENT_NMW3
-#define CQ_MOMENT_NMW3 6
+#define CQ_MOMENT_NMW3 4
 #endif
 #ifndef CQ_MOMENT_NXS3
 #define CQ_MOMENT_NXS3 2

@@ -236,11 +236,8 @@ CQ_DEVINL void moment_expand_comp(const KParams& P, const StageMeta<T, CB>& M, c
   ScatterRegs<T, CB, UNIT> S;
   S.load(P, M, e, comp);
   // per-cell constants: J = diag(J00, J11) (axis-aligned cell; checked for the whole mesh at setup)
-  const double J00 = M.X[2 * 2 + 0][e] - M.X[0][e];  // local vertex 2 is the +x neighbour (Lattice<2,1>)
-  const double J11 = M.X[1 * 2 + 1][e] - M.X[1][e];  // local vertex 1 is the +y neighbour
-  const double adet = fabs(J00 * J11);
-  const double k0 = STIFF ? fabs(J11 / J00) : adet;   // stiffness: |det|/J00^2 ; mass: |det|
-  const double k1 = STIFF ? fabs(J00 / J11) : 0.0;    // stiffness: |det|/J11^2
+  const double k0 = STIFF ? M.kc[1][e] : M.kc[0][e];  // stiffness: |det|/J00^2 ; mass: |det|  (formed by the producer)
+  const double k1 = STIFF ? M.kc[2][e] : 0.0;         // stiffness: |det|/J11^2
 
   static_for<0, DEG + 1>([&](auto A0) {
     static_for<decltype(A0)::value, DEG + 1>([&](auto C0) {

@@ -7,7 +7,9 @@
 namespace cq {
 
 // ---- producer role (one warp per stage slot) ----------------------------------------------------------
-template <class T, int G, int CB>
+// KC_ONLY (moment kernels): the consumers need the axis-aligned cell constants only, so the producer
+// gathers DIM + 1 vertex coordinates per cell instead of all of them and does not publish M.X.
+template <class T, int G, int CB, bool KC_ONLY = false>
 CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* full_bar_w, uint64_t* empty_bar_w, const int lane,
                                const int PB, const int64_t num_stages, const int slot, const int nslots, const int sub = 0,
                                const int npp = 1, uint64_t* turn_bar_w = nullptr) {
@@ -36,7 +38,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
       int32_t vid[NV];
       int32_t dof[T::RANK >= 1 ? N : 1];
       int4 pos[NP16];
-      double X[NV * DIM];
+      double X[KC_ONLY ? 2 * DIM : NV * DIM];  // KC_ONLY: vertex 0, then coordinate d of its +d neighbour
       long long rs[Meta::MAT ? N : 1];
       int rl[Meta::MAT ? N : 1];
     };
@@ -138,26 +140,26 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
               M.rowlen[i][lane] = ra.rl[i];
             }
           }
+          if constexpr (!KC_ONLY) {
 #pragma unroll
-          for (int i = 0; i < NV * DIM; ++i) M.X[i][lane] = ra.X[i];
-          if constexpr (Meta::MOM && DIM == 2) {
-            // J = diag(J00, J11): local vertex 2 is the +x neighbour, local vertex 1 the +y neighbour (Lattice<2,1>)
-            const double J00 = ra.X[2 * 2 + 0] - ra.X[0], J11 = ra.X[1 * 2 + 1] - ra.X[1];
-            M.kc[0][lane] = fabs(J00 * J11);
-            if constexpr (T::FORM_ID == CQ_FORM_STIFFNESS) {
-              M.kc[1][lane] = fabs(J11 / J00);
-              M.kc[2][lane] = fabs(J00 / J11);
-            }
+            for (int i = 0; i < NV * DIM; ++i) M.X[i][lane] = ra.X[i];
           }
-          if constexpr (Meta::MOM && DIM == 3) {
-            // hexahedron: local vertex 1 / 2 / 4 is the +x / +y / +z neighbour (Lattice<3,1>)
-            const double J00 = ra.X[1 * 3 + 0] - ra.X[0], J11 = ra.X[2 * 3 + 1] - ra.X[1], J22 = ra.X[4 * 3 + 2] - ra.X[2];
-            const double adet = fabs(J00 * J11 * J22);
+          if constexpr (Meta::MOM) {
+            // axis-aligned cells: J = diag(J_dd), J_dd = x_d(+d neighbour) - x_d(vertex 0); the only divisions of
+            // the moment kernels.  +d neighbour of local vertex 0: quadrilateral (Lattice<2,1>) vertex 2 is +x,
+            // vertex 1 is +y; hexahedron (Lattice<3,1>) vertex 1 << d.
+            double Jd[DIM], adet = 1.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+              const int nb = DIM == 2 ? (d == 0 ? 2 : 1) : (1 << d);
+              Jd[d] = (KC_ONLY ? ra.X[DIM + d] : ra.X[nb * DIM + d]) - ra.X[d];
+              adet *= Jd[d];
+            }
+            adet = fabs(adet);
             M.kc[0][lane] = adet;
             if constexpr (T::FORM_ID == CQ_FORM_STIFFNESS) {
-              M.kc[1][lane] = adet / (J00 * J00);
-              M.kc[2][lane] = adet / (J11 * J11);
-              M.kc[3][lane] = adet / (J22 * J22);
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) M.kc[1 + d][lane] = adet / (Jd[d] * Jd[d]);
             }
           }
           if constexpr (Meta::VEC) {
@@ -196,10 +198,19 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
       // ---------------- advance the pipeline: A <- B (+ level 3), B <- C (+ level 2), C <- D (+ level 1) ----
       ra = rb;
       if (ra.t >= 0 && ra.valid) {
+        if constexpr (!KC_ONLY) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v)
+          for (int v = 0; v < NV; ++v)
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) ra.X[v * DIM + d] = __ldg(P.coords + 3 * (int64_t)ra.vid[v] + d);
+            for (int d = 0; d < DIM; ++d) ra.X[v * DIM + d] = __ldg(P.coords + 3 * (int64_t)ra.vid[v] + d);
+        } else {
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            const int nb = DIM == 2 ? (d == 0 ? 2 : 1) : (1 << d);
+            ra.X[d] = __ldg(P.coords + 3 * (int64_t)ra.vid[0] + d);
+            ra.X[DIM + d] = __ldg(P.coords + 3 * (int64_t)ra.vid[nb] + d);
+          }
+        }
         if constexpr (Meta::MAT) {
           const int bs = P.bs;
 #pragma unroll
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
   double msum = 0.0;
 
   if (warp < NPW) {
-    staged_producer<T, G, CB>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages, warp, NPW);
+    staged_producer<T, G, CB, false>(P, smem_raw + (size_t)warp * stage_bytes, &full_bar[warp], &empty_bar[warp], lane, PB, num_stages, warp, NPW);
   } else {
     // =========================== consumer warps ===========================================
     const int r = lane & (G - 1), grp = lane / G;
@@ -366,7 +377,9 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
 
   if (warp < NPW * NPP) {
     const int slot = warp % NPW, sub = warp / NPW;
-    staged_producer<T, G, CB>(P, smem_raw + (size_t)slot * stage_bytes, &full_bar[slot], &empty_bar[slot], lane, PB, num_stages, slot, NPW, sub,
+    // short gather (DIM + 1 coordinates per cell) where it pays: measured, Q1 quadrilaterals are faster with the
+    // full gather (0.78 vs 0.86-0.94 ms), Q2 quadrilaterals (1.42 vs 1.44) and hexahedra (0.55 vs 0.78) with the short one
+    staged_producer<T, G, CB, (T::DIM == 3 || T::DEG == 2)>(P, smem_raw + (size_t)slot * stage_bytes, &full_bar[slot], &empty_bar[slot], lane, PB, num_stages, slot, NPW, sub,
                               NPP, &turn_bar[slot]);
   } else if (warp < NPW * NPP + NMW) {
     // ------------------------------ moment warps ------------------------------
