@@ -107,7 +107,8 @@ typedef struct cq_mesh {
   const double* coords;
   /* Optional hints from cq_mesh_classify (0 = unknown, always safe):
    *   CQ_MESH_AXIS_ALIGNED: every cell has a constant diagonal Jacobian (what create_rectangle /
-   *   create_box produce); enables the moment kernels for mass / stiffness on quadrilaterals. */
+   *   create_box produce); enables the moment kernels for mass / stiffness on quadrilaterals
+   *   (degree 1, 2) and hexahedra (degree 1). */
   int32_t flags;
 } cq_mesh;
 
