@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""CutFEM Poisson on the unit circle, Q1 quadrilaterals: the reference's demo/poisson.py
+(BASELINE.json configs[0]) on this package.
+
+Same steps as the demo: cut-cell quadrature for the level set (here customquad_b200.levelset instead
+of Algoim, demo/poisson.py:88-113), bulk stiffness + load on the uncut cells with a standard Gauss
+rule and ghost penalty on the cut-cell facets (:168-176; dolfinx in the demo), runtime-quadrature
+assembly of the cut bulk part and of the Nitsche boundary terms with quadrature normals (:180-215),
+inactive-dof locking (:229-232), a direct solve (:239-256; scipy here), L2 / H10 errors and the
+area / volume functionals through assemble_scalar (:266-290).
+
+    python examples/poisson.py -N 32        (needs a B200; prints one JSON line)
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import customquad_b200 as cq  # noqa: E402
+from customquad_b200 import cutfem, forms, utils  # noqa: E402
+from customquad_b200.levelset import generate_qr_circle  # noqa: E402
+
+
+def solve(N, betaN=10.0, betas=1.0, order=4):
+    import scipy.sparse.linalg as spla
+
+    xmin, xmax = np.array([-1.11, -1.51]), np.array([1.55, 1.22])  # demo/poisson.py:40-41
+    mesh = cq.create_rectangle([xmin, xmax], [N, N])
+    cut_cells, uncut_cells, outside_cells, qr_pts, qr_w, qr_pts_bdry, qr_w_bdry, qr_n = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    u_ex = cq.Analytic.sinprod(1.0)  # sin(pi x) sin(pi y)  (:59-67)
+    f = cq.Analytic.sinprod(2 * np.pi**2)  # -div grad u_ex  (:147)
+    g = cq.Function(V).interpolate(lambda x: np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]))  # (:146)
+
+    qr_uncut = cutfem.standard_rule(mesh, uncut_cells, 2)  # dx_uncut: dolfinx's default degree for Q1 x Q1 gradients
+    qr_bulk = [(cut_cells, qr_pts, qr_w)]
+    qr_bdry = [(cut_cells, qr_pts_bdry, qr_w_bdry, qr_n)]
+
+    # matrices: uncut bulk + cut bulk + Nitsche boundary (A = Ax + Ac1 + Ac2, :203-205)
+    A = cq.assemble_matrix(forms.stiffness(V), [qr_uncut])
+    A.assemble()
+    Ac1 = cq.assemble_matrix(forms.stiffness(V), qr_bulk)
+    Ac1.assemble()
+    Ac2 = cq.assemble_matrix(forms.nitsche(V, betaN), qr_bdry)
+    Ac2.assemble()
+    A += Ac1
+    A += Ac2
+    # right-hand side: bx + bc1 + bc2 (:208-215); load with a degree-4 rule for the sine source
+    b = cq.assemble_vector(forms.load(V, f), [cutfem.standard_rule(mesh, uncut_cells, 4)])
+    b += cq.assemble_vector(forms.load(V, f), qr_bulk)
+    b += cq.assemble_vector(forms.nitsche_rhs(V, g, betaN), qr_bdry)
+    assert np.isfinite(b.array).all() and np.isfinite(A.norm())
+
+    inactive = cutfem.get_inactive_dofs(V, cut_cells, uncut_cells)
+    A = cutfem.lock_inactive_dofs(inactive, A)
+    # ghost penalty (host, off the accelerated path) and the direct solve
+    S = cutfem.ghost_penalty_matrix(V, cutfem.ghost_penalty_facets(mesh, cut_cells, outside_cells), betas)
+    Ah = (A.to_scipy() + S).tocsc()
+    uh = cq.Function(V, spla.spsolve(Ah, b.array))
+    assert np.isfinite(uh.array).all()
+
+    def assemble(make_form):
+        m_cut = cq.assemble_scalar(make_form(), qr_bulk)
+        m_uncut = cq.assemble_scalar(make_form(), [cutfem.standard_rule(mesh, uncut_cells, 6)])
+        return m_cut + m_uncut
+
+    L2 = np.sqrt(assemble(lambda: forms.l2_error(uh, u_ex)))
+    H10 = np.sqrt(assemble(lambda: forms.h10_error(uh, u_ex)))
+    area_func = cq.assemble_scalar(forms.integral(mesh, 1.0), qr_bdry)
+    volume_func = assemble(lambda: forms.integral(mesh, 1.0))
+    return {
+        "N": N, "h": float(np.max(mesh.h())), "cut_cells": int(len(cut_cells)), "uncut_cells": int(len(uncut_cells)),
+        "L2_err": float(L2), "H10_err": float(H10),
+        "functional_volume_err": abs(volume_func - np.pi) / np.pi, "functional_area_err": abs(area_func - 2 * np.pi) / (2 * np.pi),
+        "qr_volume_err": abs(utils.volume(xmin, xmax, [N, N], uncut_cells, qr_w) - np.pi) / np.pi,
+        "qr_area_err": abs(utils.area(xmin, xmax, [N, N], qr_w_bdry) - 2 * np.pi) / (2 * np.pi),
+    }  # fmt: skip
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-N", type=int, default=32)  # demo/poisson.py:13
+    ap.add_argument("-betaN", type=float, default=10.0)
+    ap.add_argument("-betas", type=float, default=1.0)
+    a = ap.parse_args()
+    print(json.dumps(solve(a.N, a.betaN, a.betas)))
