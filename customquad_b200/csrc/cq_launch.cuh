@@ -98,12 +98,26 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "assemble_moment_split_kernel launch");
 }
 
+// lanes per entry / consumer warps of the point-by-point kernel by accumulator count (measured on Q1 hexahedra,
+// Nitsche, 128^3, U{8..27} points: G = 8, 6 warps 3.92 ms; G = 4, 8 warps 2.67 ms; 12 warps 3.8-4.8 ms (spills))
+#ifndef CQ_STAGED_G36   // 17..36 accumulators
+#define CQ_STAGED_G36 4
+#endif
+#ifndef CQ_STAGED_NCW36
+#define CQ_STAGED_NCW36 8
+#endif
+#ifndef CQ_STAGED_G45   // more than 36 accumulators
+#define CQ_STAGED_G45 8
+#endif
+#ifndef CQ_STAGED_NCW45
+#define CQ_STAGED_NCW45 4
+#endif
 // consumer warps by accumulator size: the register file holds (NPW + NCW) * 32 threads
 template <class T>
 struct StagedShape {
   static constexpr int NPW = 4;
-  static constexpr int NCW = T::NACC <= 16 ? 12 : (T::NACC <= 36 ? 6 : 4);
-  static constexpr int G = T::NACC <= 16 ? 4 : 8;
+  static constexpr int NCW = T::NACC <= 16 ? 12 : (T::NACC <= 36 ? CQ_STAGED_NCW36 : CQ_STAGED_NCW45);
+  static constexpr int G = T::NACC <= 16 ? 4 : (T::NACC <= 36 ? CQ_STAGED_G36 : CQ_STAGED_G45);
 };
 
 #ifndef CQ_MOMENT_G
