@@ -150,7 +150,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "element tensors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "csr_nnz_per_s": 2 * (pats[1].nnz + pats[2].nnz) / dt,
     }  # fmt: skip
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -327,6 +327,7 @@ def run_gpu(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     cpu = None
@@ -342,12 +343,30 @@ def run_gpu(args):
         "per_form_ms": dict(zip([f[0] for f in fl], per_form_ms)),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }  # fmt: skip
-    print(json.dumps(line))
+    # flush before any teardown: stdout is block-buffered when redirected, and a line lost to a late
+    # failure (seen once: an empty output file from a 4-GPU run whose timed region had finished) is a lost run
+    emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line of the contract, on the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    # Libraries write banners to the C stdout (NCCL prints "NCCL version ..." on the first collective):
+    # keep file descriptor 1 for the JSON line alone and send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
