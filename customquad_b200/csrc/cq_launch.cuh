@@ -67,7 +67,7 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   using Lay = StagedLayout<T, CB>;
   auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW, XT, NPP>;
   const size_t budget = (size_t)ctx->max_smem_optin - 1024;
-  const size_t per_point = (size_t)T::DIM * 8 + 8;
+  const size_t per_point = (size_t)T::DIM * 8 * (T::NEED_NORMAL ? 2 : 1) + 8;
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
   if (budget / NPW <= fixed + 64 * per_point) { set_error("moment kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
   const int64_t pb_max = (int64_t)((budget / NPW - fixed) / per_point) & ~(int64_t)1;
@@ -78,7 +78,8 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   if (pb < 64) pb = 64;
   if constexpr (XT) {
     // the expansion tiles of a stage reuse its point buffer: it has to hold (DEG + 1) of them
-    const int64_t need = (int64_t)(((T::DEG + 1) * RowTile<T::DIM, T::DEG>::bytes(CB) + T::DIM * 8 - 1) / (T::DIM * 8));
+    // (the tiles may run over the weights / normals that follow the points: all dead by then)
+    const int64_t need = (int64_t)(((T::DEG + 1) * RowTile<T::DIM, T::DEG>::bytes(CB) + per_point - 1) / per_point);
     if (pb < need) pb = (need + 1) & ~(int64_t)1;
     if (pb > pb_max) { set_error("moment kernel: expansion tiles do not fit the stage"); return CQ_ERR_UNSUPPORTED; }
   }
@@ -147,6 +148,12 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NXS3
 #define CQ_MOMENT_NXS3 2
 #endif
+#ifndef CQ_NITSCHE_NMW3  // Nitsche moment kernel (Q1 hexahedra): moment warps / expansion sets (3 stage slots)
+#define CQ_NITSCHE_NMW3 6
+#endif
+#ifndef CQ_NITSCHE_NXS3
+#define CQ_NITSCHE_NXS3 1
+#endif
 #ifndef CQ_MOMENT_NPP  // producer warps per stage slot
 #define CQ_MOMENT_NPP 1
 #endif
@@ -174,6 +181,14 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1>(ctx, P, s);
         return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
       }
+    }
+    // symmetric Nitsche form with quadrature normals on Q1 hexahedra: 4 moment sets (w, w n_d), one lane of the entry's
+    // group per set.  Three stage slots (108 moments per entry in the header).  Not used for quadrilaterals: measured on
+    // the bench-size Q1 mesh the point-by-point kernel is faster there (1.77 vs 4.2 ms: its per-point work is small and
+    // it splits the points over the lanes, the moment sets run every point in every lane).
+    if constexpr (T::FORM_ID == CQ_FORM_NITSCHE && T::DEG == 1 && T::DIM == 3) {
+      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3)
+        return launch_moment_split<T, 4, 3, CQ_NITSCHE_NMW3, CQ_NITSCHE_NXS3 * 2, true>(ctx, P, s);
     }
     // ... and on Q1 hexahedra (create_box meshes): 27 moments, two expansion roles
     if constexpr (T::DIM == 3 && T::DEG == 1 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {

@@ -58,6 +58,13 @@ struct Poly1D {
       if (p - u >= 0 && p - u <= DEG) s += L(a, u) * L(c, p - u);
     return s;
   }
+  // d/dt (l_a l_c): derivative of the product polynomial
+  CQ_HD static constexpr double RD(int a, int c, int p) { return p + 1 < P ? (p + 1) * R00(a, c, p + 1) : 0.0; }
+  // KIND 0: l_a l_c, 1: (l_a l_c)'
+  template <int KIND>
+  CQ_HD static constexpr double RK(int a, int c, int p) {
+    return KIND == 0 ? R00(a, c, p) : RD(a, c, p);
+  }
   CQ_HD static constexpr double R11(int a, int c, int p) {
     double s = 0.0;
     for (int u = 0; u < DEG; ++u)
@@ -202,8 +209,76 @@ CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const 
   }
 }
 
+// Nitsche: lane r of the entry's group of four owns moment set r (weights w, w n_0, w n_1 (, w n_2)) and runs
+// over ALL points of the entry: no cross-lane reduction, and the point itself is a shared-memory broadcast.
+template <class T, int CB>
+CQ_DEVINL void moment_accumulate_sets(StageMeta<T, CB>& M, const int e, const bool active, const bool compute, const int r) {
+  using Meta = StageMeta<T, CB>;
+  constexpr int DIM = T::DIM, Pn = Meta::PN, NM1 = Meta::NM1, NSET = Meta::NSET;
+  double acc[NM1];
+#pragma unroll
+  for (int k = 0; k < NM1; ++k) acc[k] = 0.0;
+  const bool mine = active && r < NSET;
+  const int nq = (mine && compute) ? M.nq[e] : 0;
+  const double* pp = M.pts[e];
+  const double* wp = M.w[e];
+  const double* np_ = M.nrm[e];
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    double w = wp[q];
+    if (r > 0) w *= np_[DIM * q + (r - 1)];
+    if constexpr (DIM == 2) {
+      const double2 xy = *reinterpret_cast<const double2*>(pp + 2 * q);
+      const double tx = xy.x - 0.5, ty = xy.y - 0.5;
+      double X[Pn], WY[Pn];
+      X[0] = 1.0; X[1] = tx;
+      WY[0] = w; WY[1] = w * ty;
+#pragma unroll
+      for (int p = 2; p < Pn; ++p) {
+        X[p] = X[p - 1] * tx;
+        WY[p] = WY[p - 1] * ty;
+      }
+#pragma unroll
+      for (int b = 0; b < Pn; ++b) acc[b] += WY[b];
+#pragma unroll
+      for (int a = 1; a < Pn; ++a)
+#pragma unroll
+        for (int b = 0; b < Pn; ++b) acc[a * Pn + b] = fma(X[a], WY[b], acc[a * Pn + b]);
+    } else {
+      static_assert(DIM == 2 || Pn == 3, "hexahedra: degree 1");
+      const double t0 = pp[3 * q] - 0.5, t1 = pp[3 * q + 1] - 0.5, t2 = pp[3 * q + 2] - 0.5;
+      double Z[3], YZ[3][3];
+      Z[0] = w; Z[1] = w * t2; Z[2] = Z[1] * t2;
+      const double t11 = t1 * t1, t00 = t0 * t0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        YZ[0][c] = Z[c];
+        YZ[1][c] = t1 * Z[c];
+        YZ[2][c] = t11 * Z[c];
+      }
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          acc[(0 * 3 + b) * 3 + c] += YZ[b][c];
+          acc[(1 * 3 + b) * 3 + c] = fma(t0, YZ[b][c], acc[(1 * 3 + b) * 3 + c]);
+          acc[(2 * 3 + b) * 3 + c] = fma(t00, YZ[b][c], acc[(2 * 3 + b) * 3 + c]);
+        }
+    }
+  }
+  if (mine) {
+#pragma unroll
+    for (int k = 0; k < NM1; ++k) M.mu[r * NM1 + k][e] = acc[k];
+  }
+}
+
 template <class T, int G, int CB>
 CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const bool active, const bool compute, const int r) {
+  if constexpr (StageMeta<T, CB>::NIT) {
+    static_assert(!StageMeta<T, CB>::NIT || G == 4, "Nitsche moment sets: four lanes per entry");
+    moment_accumulate_sets<T, CB>(M, e, active, compute, r);
+    return;
+  } else {
   constexpr int Pn = 2 * T::DEG + 1, NM = StageMeta<T, CB>::NMOM;
   constexpr int MPAD = round_up(NM, G), B = MPAD / G;
   double acc[MPAD];
@@ -220,6 +295,7 @@ CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const b
 #pragma unroll
     for (int kk = 0; kk < B; ++kk)
       if (r * B + kk < NM) M.mu[r * B + kk][e] = acc[kk];
+  }
   }
 }
 
@@ -415,9 +491,146 @@ CQ_DEVINL void moment_expand_rows3(const StageMeta<T, CB>& M, const int e, doubl
   });
 }
 
+// Symmetric Nitsche form on an axis-aligned cell (J = diag(J_dd)):
+//   A_ij = sum_q w |det J| [ -(n.G_j) psi_i - psi_j (n.G_i) + betaN/h psi_i psi_j ],  n.G_i = sum_d n_d d_d psi_i / J_dd
+//        = gamma W[psi_i psi_j] - sum_d kappa_d N_d[ d_d (psi_i psi_j) ],
+// W[f] = sum w f, N_d[f] = sum w n_d f, gamma = |det J| betaN / h_K, kappa_d = |det J| / J_dd (kc, producer).
+// Each term is a mass-like contraction of one moment set, with the derivative rows RD in dimension d.
+template <class T, int CB, int A0>
+CQ_DEVINL void moment_expand_rows_nitsche(const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
+  using Meta = StageMeta<T, CB>;
+  constexpr int DIM = T::DIM, DEG = T::DEG, D1 = DEG + 1, Pn = Meta::PN, NM1 = Meta::NM1;
+  using Q = Poly1D<DEG>;
+  const double gam = M.kc[1 + DIM][e];
+  double kap[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) kap[d] = M.kc[1 + d][e];
+  if constexpr (DIM == 2) {
+    static_for<0, D1>([&](auto C0) {
+      constexpr int c0 = decltype(C0)::value;
+      // x contraction of the three sets: (W, R00), (N0, RD), (N1, R00)
+      double U[3][Pn];
+      static_for<0, 3>([&](auto SS) {
+        constexpr int set = decltype(SS)::value;
+        bool init = false;
+        static_for<0, Pn>([&](auto PP) {
+          constexpr int p = decltype(PP)::value;
+          constexpr double rc = Q::template RK<(set == 1) ? 1 : 0>(A0, c0, p);
+          if constexpr (rc != 0.0) {
+#pragma unroll
+            for (int q = 0; q < Pn; ++q) {
+              const double m = M.mu[set * NM1 + p * Pn + q][e];
+              U[set][q] = init ? fma(rc, m, U[set][q]) : rc * m;
+            }
+            init = true;
+          }
+        });
+        if (!init) {
+#pragma unroll
+          for (int q = 0; q < Pn; ++q) U[set][q] = 0.0;
+        }
+      });
+      static_for<0, D1>([&](auto A1) {
+        static_for<0, D1>([&](auto C1) {
+          constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
+          double mW = 0.0, m0 = 0.0, m1 = 0.0;
+          static_for<0, Pn>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            constexpr double r00 = Q::R00(a1, c1, q), rd = Q::RD(a1, c1, q);
+            if constexpr (r00 != 0.0) {
+              mW = fma(r00, U[0][q], mW);
+              m0 = fma(r00, U[1][q], m0);
+            }
+            if constexpr (rd != 0.0) m1 = fma(rd, U[2][q], m1);
+          });
+          tile[(a1 * D1 + c0) * D1 + c1] = fma(gam, mW, -fma(kap[0], m0, kap[1] * m1));
+        });
+      });
+    });
+  } else {
+    static_assert(DIM == 2 || DEG == 1, "hexahedra: degree 1");
+    static_for<0, 2>([&](auto C0) {
+      constexpr int c0 = decltype(C0)::value;
+      // x: (W, R00), (N0, RD), (N1, R00), (N2, R00)
+      double U[4][3][3];
+      static_for<0, 4>([&](auto SS) {
+        constexpr int set = decltype(SS)::value;
+        bool init = false;
+        static_for<0, 3>([&](auto PP) {
+          constexpr int p = decltype(PP)::value;
+          constexpr double rc = Q::template RK<(set == 1) ? 1 : 0>(A0, c0, p);
+          if constexpr (rc != 0.0) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const double m = M.mu[set * NM1 + (p * 3 + q) * 3 + r][e];
+                U[set][q][r] = init ? fma(rc, m, U[set][q][r]) : rc * m;
+              }
+            init = true;
+          }
+        });
+        if (!init) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) U[set][q][r] = 0.0;
+        }
+      });
+      static_for<0, 2>([&](auto A1) {
+        static_for<0, 2>([&](auto C1) {
+          constexpr int a1 = decltype(A1)::value, c1 = decltype(C1)::value;
+          // y: RD for the N1 set, R00 for the others
+          double V[4][3];
+#pragma unroll
+          for (int st = 0; st < 4; ++st)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) V[st][r] = 0.0;
+          static_for<0, 3>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            constexpr double r00 = Q::R00(a1, c1, q), rd = Q::RD(a1, c1, q);
+            if constexpr (r00 != 0.0) {
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                V[0][r] = fma(r00, U[0][q][r], V[0][r]);
+                V[1][r] = fma(r00, U[1][q][r], V[1][r]);
+                V[3][r] = fma(r00, U[3][q][r], V[3][r]);
+              }
+            }
+            if constexpr (rd != 0.0) {
+#pragma unroll
+              for (int r = 0; r < 3; ++r) V[2][r] = fma(rd, U[2][q][r], V[2][r]);
+            }
+          });
+          static_for<0, 2>([&](auto A2) {
+            static_for<0, 2>([&](auto C2) {
+              constexpr int a2 = decltype(A2)::value, c2 = decltype(C2)::value;
+              double mW = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+              static_for<0, 3>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                constexpr double r00 = Q::R00(a2, c2, r), rd = Q::RD(a2, c2, r);
+                if constexpr (r00 != 0.0) {
+                  mW = fma(r00, V[0][r], mW);
+                  m0 = fma(r00, V[1][r], m0);
+                  m1 = fma(r00, V[2][r], m1);
+                }
+                if constexpr (rd != 0.0) m2 = fma(rd, V[3][r], m2);
+              });
+              tile[(a1 + 2 * a2) * 8 + (c0 + 2 * c1 + 4 * c2)] = fma(gam, mW, -fma(kap[0], m0, fma(kap[1], m1, kap[2] * m2)));
+            });
+          });
+        });
+      });
+    });
+  }
+}
+
 template <class T, int CB, int A0>
 CQ_DEVINL void moment_expand_rows(const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
-  if constexpr (T::DIM == 3) {
+  if constexpr (StageMeta<T, CB>::NIT) {
+    moment_expand_rows_nitsche<T, CB, A0>(M, e, tile);
+    return;
+  } else if constexpr (T::DIM == 3) {
     moment_expand_rows3<T, CB, A0>(M, e, tile);
     return;
   } else {

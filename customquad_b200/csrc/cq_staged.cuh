@@ -80,12 +80,18 @@ struct StageMeta {
   double coef[T::NEED_COEF ? T::NCOEF : 1][CB];
   // monomial moments handed from the moment warps to the expansion warps (cq_moment.cuh, split kernel)
   // (quadrilaterals of degree 1 and 2, hexahedra of degree 1)
-  static constexpr bool MOMF = T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS;
+  // The symmetric Nitsche form carries DIM + 1 moment sets: weights w and w n_d (quadrature normals).
+  static constexpr bool NIT = T::FORM_ID == CQ_FORM_NITSCHE;
+  static constexpr bool MOMF = T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS || NIT;
   static constexpr bool MOM = MOMF && (T::DIM == 2 || (T::DIM == 3 && T::DEG == 1));
   static constexpr int PN = 2 * T::DEG + 1;
-  static constexpr int NMOM = MOM ? (T::DIM == 2 ? PN * PN : PN * PN * PN) : 1;
+  static constexpr int NM1 = T::DIM == 2 ? PN * PN : PN * PN * PN;  // moments per set
+  static constexpr int NSET = NIT ? T::DIM + 1 : 1;
+  static constexpr int NMOM = MOM ? NSET * NM1 : 1;
   double mu[NMOM][CB];
-  double kc[MOM ? 4 : 1][CB];  // axis-aligned cell constants: |det J|, |det J|/J_dd^2 for d = 0..DIM-1 (producer)
+  // axis-aligned cell constants (producer): [0] |det J|; stiffness: [1 + d] |det J| / J_dd^2;
+  // Nitsche: [1 + d] |det J| / J_dd (signed), [1 + DIM] |det J| betaN / h_K
+  double kc[MOM ? 5 : 1][CB];
 };
 
 template <class T, int CB>

@@ -161,6 +161,15 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
 #pragma unroll
               for (int d = 0; d < DIM; ++d) M.kc[1 + d][lane] = adet / (Jd[d] * Jd[d]);
             }
+            if constexpr (Meta::NIT) {
+              double h2 = 0.0;  // ufl.CellDiameter of a box: its diagonal
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) {
+                M.kc[1 + d][lane] = adet / Jd[d];
+                h2 = fma(Jd[d], Jd[d], h2);
+              }
+              M.kc[1 + DIM][lane] = adet * P.betaN / sqrt(h2);
+            }
           }
           if constexpr (Meta::VEC) {
 #pragma unroll
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
     const int slot = warp % NPW, sub = warp / NPW;
     // short gather (DIM + 1 coordinates per cell) where it pays: measured, Q1 quadrilaterals are faster with the
     // full gather (0.78 vs 0.86-0.94 ms), Q2 quadrilaterals (1.42 vs 1.44) and hexahedra (0.55 vs 0.78) with the short one
-    staged_producer<T, G, CB, (T::DIM == 3 || T::DEG == 2)>(P, smem_raw + (size_t)slot * stage_bytes, &full_bar[slot], &empty_bar[slot], lane, PB, num_stages, slot, NPW, sub,
+    staged_producer<T, (Meta::NIT ? 1 : G), CB, (T::DIM == 3 || T::DEG == 2 || Meta::NIT)>(P, smem_raw + (size_t)slot * stage_bytes, &full_bar[slot], &empty_bar[slot], lane, PB, num_stages, slot, NPW, sub,
                               NPP, &turn_bar[slot]);
   } else if (warp < NPW * NPP + NMW) {
     // ------------------------------ moment warps ------------------------------

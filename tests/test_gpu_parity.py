@@ -191,7 +191,7 @@ def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
     V = cq.FunctionSpace(mesh, ("Lagrange", degree)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", degree))
     rng = np.random.default_rng(31)
     cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 40)])
-    qr = synthetic_ragged(cells, 2, 0, 70, seed=13)
+    qr = synthetic_ragged(cells, 2, 0, 70, seed=13, normals=True)
     for form in (forms.mass(V), forms.stiffness(V)):
         R = oracle_backend.matrix(form, [qr])
         set_variant(0)
@@ -216,8 +216,8 @@ def test_moment_kernel_hexahedra(cuda_backend, oracle_backend, bs):
     V = cq.FunctionSpace(mesh, ("Lagrange", 1)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", 1))
     rng = np.random.default_rng(37)
     cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 40), np.arange(mesh.num_cells)])
-    qr = synthetic_ragged(cells, 3, 0, 40, seed=17)
-    for form in (forms.mass(V), forms.stiffness(V)):
+    qr = synthetic_ragged(cells, 3, 0, 40, seed=17, normals=True)
+    for form in (forms.mass(V), forms.stiffness(V), forms.nitsche(V, 10.0)):
         R = oracle_backend.matrix(form, [qr])
         set_variant(0)
         A = cuda_backend.matrix(form, [qr])
