@@ -81,7 +81,8 @@ struct StageMeta {
   // monomial moments handed from the moment warps to the expansion warps (cq_moment.cuh, split kernel)
   // (quadrilaterals of degree 1 and 2, hexahedra of degree 1)
   // The symmetric Nitsche form carries DIM + 1 moment sets: weights w and w n_d (quadrature normals).
-  static constexpr bool NIT = T::FORM_ID == CQ_FORM_NITSCHE;
+  // (hexahedra only: on quadrilaterals the point-by-point kernel is faster, and the header space is needed for points)
+  static constexpr bool NIT = T::FORM_ID == CQ_FORM_NITSCHE && T::DIM == 3 && T::DEG == 1;
   static constexpr bool MOMF = T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS || NIT;
   static constexpr bool MOM = MOMF && (T::DIM == 2 || (T::DIM == 3 && T::DEG == 1));
   static constexpr int PN = 2 * T::DEG + 1;
