@@ -159,6 +159,7 @@ def workload_config(n_gpus):
         "cells_per_gpu": MESH_N * MESH_N, "forms": [f[0] for f in FORMS], "mean_points_per_cell": (NQ_LO + NQ_HI) / 2,
         "l2": "inputs (>= 4 GB of points per pass) are larger than the 126 MB L2; no explicit flush",
         "parallelism": f"cells{n_gpus}" if n_gpus > 1 else "single",
+        "exchange": "interface rows of the neighbour rank: red.global.add.f64 into peer memory over NVLink from the assembly kernels (CQ_PEER_SCATTER=0: NCCL send/recv + accumulate kernel)" if n_gpus > 1 else "none",
     }  # fmt: skip
 
 
@@ -212,8 +213,17 @@ def run_gpu(args):
             ex = cqdist.SlabExchange(spaces[deg], slab)
             ex.set_pattern(mats[name].indptr, mats[name].indices)
             exch[name] = ex
+        # fused exchange: the assembly kernels add the interface rows straight into the owner's matrix over
+        # NVLink (peer memory); falls back to the NCCL send/recv + accumulate path if peer mapping fails
+        if os.environ.get("CQ_PEER_SCATTER", "1") != "0":
+            fused = all([exch[name].enable_peer_scatter(mats[name]) for name, _, _ in fl])
+            if not fused:
+                for name in mats:
+                    mats[name].peer_row0, mats[name].peer_rowstart = None, None
+                    exch[name].peer = False
+            log(f"interface exchange: {'peer RED over NVLink (fused in the assembly kernels)' if fused else 'NCCL send/recv'}")
     asm.qr_on_device(qr, dev)  # inputs resident in HBM before the timed region
-    ctx_launch0 = None
+    fused = exch is not None and all(getattr(e, "peer", False) for e in exch.values())
 
     def step(events=None):
         for i, (name, form, _) in enumerate(fl):
@@ -221,9 +231,11 @@ def run_gpu(args):
             if events is not None:
                 events[i][0].record()
             A.data.zero_()  # A.zeroEntries() (assemble_matrix.py:20)
+            if fused:
+                exch[name].fence(dev)  # the neighbour's kernel adds into this matrix: it must be zeroed first
             asm.assemble_matrix(form, [qr], A=A)
             if exch is not None:
-                exch[name].exchange_matrix(A.data)
+                exch[name].exchange_matrix(A.data)  # fused: only the completion fence
             if events is not None:
                 events[i][1].record()
 
@@ -299,11 +311,15 @@ def run_gpu(args):
         hq_np = RaggedQuadrature(hq.cells.numpy(), hq.offsets.numpy(), hq.pts.numpy(), hq.w.numpy(), None, 2)
         vals = {name: torch.empty(mats[name].nnz, dtype=torch.float64).pin_memory() for name in mats}
 
+        saved = {name: (mats[name].peer_row0, mats[name].peer_rowstart) for name in mats}
+        for name in mats:  # the host-buffer call zeroes inside the call: it uses the NCCL exchange
+            mats[name].peer_row0, mats[name].peer_rowstart = None, None
+
         def e2e_step():
             for name, form, _ in fl:
                 asm.assemble_matrix_host(form, hq_np, mats[name], vals[name])
                 if exch is not None:
-                    exch[name].exchange_matrix(mats[name].data)
+                    exch[name].exchange_matrix(mats[name].data, force_nccl=True)
 
         log("e2e: warm-up")
         for _ in range(2):
@@ -320,6 +336,8 @@ def run_gpu(args):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        for name in mats:
+            mats[name].peer_row0, mats[name].peer_rowstart = saved[name]
         h2d = len(fl) * (qr.cells.nbytes + qr.offsets.nbytes + qr.pts.nbytes + qr.w.nbytes)
         d2h = sum(8 * mats[name].nnz for name in mats)
         e2e = {"value": len(fl) * C_cells * world / dt, "unit": "element tensors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -32,7 +32,11 @@ class QuadratureDesc(C.Structure):
 
 
 class CsrDesc(C.Structure):
-    _fields_ = [("num_rows", C.c_int64), ("nnz", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p)]
+    _fields_ = [("num_rows", C.c_int64), ("nnz", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p),
+                ("peer_row0", C.c_int64), ("peer_rowstart", C.c_void_p)]  # fmt: skip
+
+    def __init__(self, num_rows=0, nnz=0, indptr=None, indices=None, values=None, peer_row0=None, peer_rowstart=None):
+        super().__init__(num_rows, nnz, indptr, indices, values, num_rows if peer_row0 is None else peer_row0, peer_rowstart)
 
 
 class CqError(RuntimeError):
@@ -64,6 +68,9 @@ _SIGNATURES = {
     "cq_element_tensors": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_csr_accumulate_rows": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_axpy": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "cq_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cq_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cq_assemble_matrix_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_vector_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),

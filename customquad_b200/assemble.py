@@ -174,7 +174,8 @@ def create_matrix(form: Form, pattern_cells=None) -> CSRMatrix:
 
 
 def _csr_desc(A: CSRMatrix):
-    return _lib.CsrDesc(A.shape[0], A.nnz, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data))
+    return _lib.CsrDesc(A.shape[0], A.nnz, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data),
+                        getattr(A, "peer_row0", None), _ptr(getattr(A, "peer_rowstart", None)))
 
 
 def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: str = "form") -> CSRMatrix:

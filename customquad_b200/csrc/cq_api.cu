@@ -24,6 +24,25 @@ int check_cuda(cudaError_t e, const char* what) {
   return CQ_ERR_CUDA;
 }
 
+// base address and size of the allocation containing p (driver API cuMemGetAddressRange, resolved through the
+// runtime so that the library keeps linking against libcudart only)
+static int cuMemGetAddressRange_fallback(const void* p, void** base, size_t* size) {
+  typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+  static fn_t fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return -1;
+    fn = reinterpret_cast<fn_t>(f);
+  }
+  unsigned long long b = 0;
+  size_t s = 0;
+  if (fn(&b, &s, (unsigned long long)(uintptr_t)p) != 0) return -1;
+  *base = reinterpret_cast<void*>((uintptr_t)b);
+  *size = s;
+  return 0;
+}
+
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 static int gdim_of(int cell_type) { return cell_type == CQ_CELL_QUADRILATERAL ? 2 : 3; }
@@ -60,6 +79,7 @@ static int pack(cq_ctx* ctx, const cq_form_desc* f, const cq_mesh* mesh, const c
     return CQ_ERR_ALIGN;
   }
   memset(&P, 0, sizeof P);
+  P.peer_row0 = 0x7fffffffffffffffLL;
   P.num_entries = qr->num_entries;
   P.cells = qr->cells; P.offsets = qr->offsets; P.pts = qr->pts; P.w = qr->weights; P.normals = qr->normals;
   P.geom_dofmap = mesh->geom_dofmap; P.coords = mesh->coords;
@@ -263,6 +283,12 @@ int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
   if (qr->num_entries == 0) return CQ_OK;
   if (int rc = set_device(ctx)) return rc;
   P.indptr = A->indptr; P.indices = A->indices; P.values = A->values;
+  if (A->peer_rowstart) {
+    if (A->peer_row0 < 0 || A->peer_row0 > A->num_rows) { set_error("peer_row0 out of range"); return CQ_ERR_INVALID; }
+    if (!space->elem_pos || ctx->variant == 1) { set_error("peer scatter needs the scatter map (staged kernels)"); return CQ_ERR_UNSUPPORTED; }
+    P.peer_row0 = A->peer_row0;
+    P.peer_rowstart = reinterpret_cast<const long long*>(A->peer_rowstart);
+  }
   return launch_matrix(ctx, *form, P, static_cast<cudaStream_t>(stream));
 }
 
@@ -398,6 +424,38 @@ int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t n
   accumulate_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A->values, A->indptr, row0, nrows, recv_indptr, recv);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "accumulate_rows_kernel launch");
+}
+
+int cq_ipc_export(cq_ctx* ctx, const void* dev_ptr, unsigned char handle[64], int64_t* offset) {
+  if (!ctx || !dev_ptr || !handle || !offset) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (int rc = check_cuda(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)), "cudaIpcGetMemHandle")) return rc;
+  void* base = nullptr;
+  size_t size = 0;
+  if (cuMemGetAddressRange_fallback(dev_ptr, &base, &size) != 0) { set_error("cannot find the allocation base of the pointer"); return CQ_ERR_CUDA; }
+  memcpy(handle, &h, 64);
+  *offset = (int64_t)((const char*)dev_ptr - (const char*)base);
+  return CQ_OK;
+}
+
+int cq_ipc_open(cq_ctx* ctx, const unsigned char handle[64], int64_t offset, void** mapped_ptr, void** mapped_base) {
+  if (!ctx || !handle || !mapped_ptr || !mapped_base || offset < 0) { set_error("bad argument"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* base = nullptr;
+  if (int rc = check_cuda(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return rc;
+  *mapped_base = base;
+  *mapped_ptr = (char*)base + offset;
+  return CQ_OK;
+}
+
+int cq_ipc_close(cq_ctx* ctx, void* mapped_base) {
+  if (!ctx || !mapped_base) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  return check_cuda(cudaIpcCloseMemHandle(mapped_base), "cudaIpcCloseMemHandle");
 }
 
 int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream) {

@@ -28,6 +28,8 @@ struct KParams {
   const int64_t* __restrict__ indptr;
   const int32_t* __restrict__ indices;
   double* values;  // CSR values (matrix)
+  long long peer_row0;                         // rows >= peer_row0 are scattered into a neighbour's matrix (cq_csr)
+  const long long* __restrict__ peer_rowstart; // [num_rows - peer_row0 + 1], relative to `values`
   double* out;     // vector b / scalar m / element tensors
   int* err_flag;
   const uint8_t* __restrict__ elem_pos;  // scatter positions [num_cells, NPOS] or null

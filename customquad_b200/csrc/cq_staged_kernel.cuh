@@ -224,9 +224,12 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           const int bs = P.bs;
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            const long long rs = __ldg(P.indptr + (int64_t)ra.dof[i] * bs);
+            // rows owned by the neighbour rank: slot table of ITS matrix (peer memory over NVLink)
+            const long long row = (long long)ra.dof[i] * bs;
+            const long long* ip = row >= P.peer_row0 ? P.peer_rowstart + (row - P.peer_row0) : reinterpret_cast<const long long*>(P.indptr) + row;
+            const long long rs = __ldg(ip);
             ra.rs[i] = rs;
-            ra.rl[i] = bs == 1 ? 0 : (int)(__ldg(P.indptr + (int64_t)ra.dof[i] * bs + 1) - rs);
+            ra.rl[i] = bs == 1 ? 0 : (int)(__ldg(ip + 1) - rs);
           }
         }
       }

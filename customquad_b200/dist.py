@@ -128,10 +128,14 @@ class SlabExchange:
             ip = _to_numpy(indptr[self.send_row0 : self.nrows + 1])
             self.send_lo, self.send_hi = int(ip[0]), int(ip[-1])
 
-    def exchange_matrix(self, values):
+    def exchange_matrix(self, values, force_nccl=False):
         """values: this rank's CSR data (torch tensor).  After the call the owned rows are complete."""
         import torch
         import torch.distributed as dist
+
+        if getattr(self, "peer", False) and not force_nccl:  # the kernels already scattered into the owner's memory
+            self.fence(values.device)
+            return
 
         ops, recv = [], None
         if self.has_up:
@@ -146,6 +150,75 @@ class SlabExchange:
             if self.recv_indptr is None or self.recv_indptr.device != values.device:
                 self.recv_indptr = torch.from_numpy(self.recv_indptr_host).to(values.device)
             (self._acc_rows or _cuda_accumulate_rows)(values, self.indptr, self.recv_row0, self.line, self.recv_indptr, recv)
+
+    # -- matrices, fused: the kernel scatters the interface rows into the owner's memory ---------
+    def enable_peer_scatter(self, A):
+        """One-time setup for matrix `A` (same pattern as set_pattern): map the value array of rank+1 into
+        this process (CUDA IPC, include/cq_b200.h cq_ipc_*) and build the slot table that makes the assembly
+        kernels add this rank's contributions to its top lattice line -- owned by rank+1 -- straight into
+        rank+1's matrix with red.global.add.f64 over NVLink.  After this, ``exchange_matrix`` is only the
+        completion barrier.  Returns False (and leaves the NCCL exchange in place) if peer memory cannot
+        be mapped.  Collective over the group."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        L = _lib.load()
+        dev = A.data.device
+        ctx = _lib.ctx(dev.index)
+        rank, world = self.slab.rank, self.slab.world
+        # what the lower neighbour needs from me: IPC handle of my values + the starts of my interface rows
+        mine = None
+        ok = True
+        try:
+            if self.has_down:
+                handle = (C.c_ubyte * 64)()
+                off = C.c_int64(0)
+                _lib.check(L.cq_ipc_export(ctx, C.c_void_p(A.data.data_ptr()), handle, C.byref(off)))
+                rows = _to_numpy(A.indptr[self.recv_row0 : self.recv_row0 + self.line + 1]).astype(np.int64)
+                mine = (bytes(handle), int(off.value), rows)
+        except Exception:  # noqa: BLE001 -- any failure => everybody falls back
+            ok = False
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, mine), group=self.group)
+        if not all(g[0] for g in gathered):
+            return False
+        ok = True
+        if self.has_up:
+            try:
+                handle, off, rows = gathered[rank + 1][1]
+                ptr, base = C.c_void_p(), C.c_void_p()
+                hbuf = (C.c_ubyte * 64).from_buffer_copy(handle)
+                _lib.check(L.cq_ipc_open(ctx, hbuf, off, C.byref(ptr), C.byref(base)))
+                delta = ptr.value - A.data.data_ptr()
+                assert delta % 8 == 0
+                # sender row j of the top line is a prefix of the owner's row: same position inside the row
+                table = rows + delta // 8
+                self._peer_base = base
+                A.peer_row0 = int(self.send_row0)
+                A.peer_rowstart = torch.from_numpy(table).to(dev)
+            except Exception:  # noqa: BLE001
+                ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=self.group)
+        if not all(flags):
+            A.peer_row0, A.peer_rowstart = None, None
+            return False
+        self.peer = True
+        return True
+
+    def fence(self, device):
+        """Stream-ordered barrier over the group: every rank's work enqueued so far (the zeroing of its
+        matrix, or its assembly kernels with their peer REDs) is complete on all ranks' streams afterwards."""
+        import torch
+        import torch.distributed as dist
+
+        if not hasattr(self, "_fence_buf") or self._fence_buf.device != device:
+            self._fence_buf = torch.zeros(1, dtype=torch.float32, device=device)
+        dist.all_reduce(self._fence_buf, group=self.group)
 
     # -- vectors ----------------------------------------------------------------------------
     def exchange_vector(self, b):

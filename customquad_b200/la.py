@@ -18,6 +18,10 @@ class CSRMatrix:
         self._stream_ptr = stream_ptr
         self.assembled = False
         self.full_pattern = True  # pattern of every cell of the mesh (create_matrix(form))
+        # multi-GPU peer scatter (dist.SlabExchange.enable_peer_scatter): rows >= peer_row0 are added straight
+        # into the owner rank's values over NVLink; peer_rowstart is the device slot table (cq_csr)
+        self.peer_row0 = None
+        self.peer_rowstart = None
 
     @property
     def size(self):

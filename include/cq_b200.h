@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CQ_B200_ABI_VERSION 1
+#define CQ_B200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------ */
 typedef enum cq_status {
@@ -154,6 +154,16 @@ typedef struct cq_csr {
   const int64_t* indptr;   /* [num_rows + 1] */
   const int32_t* indices;  /* [nnz] */
   double* values;          /* [nnz] -- accumulated into (ADD_VALUES); caller zeroes */
+  /* Optional (multi-GPU, cell-partitioned assembly): the rows >= peer_row0 of this matrix are owned by a
+   * neighbour rank.  With peer_rowstart != NULL the kernels add the contributions to those rows straight
+   * into the owner's value array over NVLink (red.global.add.f64 on peer memory) instead of into `values`:
+   * the slot of entry p of row r >= peer_row0 is values + peer_rowstart[r - peer_row0] + p, where
+   * peer_rowstart (device, [num_rows - peer_row0 + 1] int64) already contains the distance between the
+   * two allocations in doubles (customquad_b200/dist.py builds it from a cq_ipc_open'ed pointer).  This
+   * replaces the separate stash exchange of PETSc's MatAssemblyBegin/End (README.md:95).  Set
+   * peer_row0 = num_rows and peer_rowstart = NULL when unused. */
+  int64_t peer_row0;
+  const int64_t* peer_rowstart;
 } cq_csr;
 
 typedef struct cq_ctx cq_ctx;
@@ -217,6 +227,14 @@ int cq_csr_accumulate_rows(cq_ctx* ctx, const cq_csr* A, int64_t row0, int64_t n
                            const int64_t* recv_indptr, const double* recv, void* stream);
 /* y[i] += x[i], i < n (vector interface dofs) */
 int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream);
+
+/* ---- peer memory (one process per GPU) --------------------------------------------------------
+ * cq_ipc_export: the 64-byte CUDA IPC handle of the allocation containing dev_ptr and dev_ptr's byte
+ * offset inside it; cq_ipc_open (in the neighbour's process, on its own ctx): map that allocation and
+ * return the address of the same byte there (peer access is enabled lazily); cq_ipc_close unmaps. */
+int cq_ipc_export(cq_ctx* ctx, const void* dev_ptr, unsigned char handle[64], int64_t* offset);
+int cq_ipc_open(cq_ctx* ctx, const unsigned char handle[64], int64_t offset, void** mapped_ptr, void** mapped_base);
+int cq_ipc_close(cq_ctx* ctx, void* mapped_base);
 
 /* ---- end-to-end entry points (HOST pointers; copies are part of the call) ------------------
  * The reference-facing call with host buffers: qr arrays, and the result, live in (ideally

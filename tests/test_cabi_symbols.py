@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/cq_b200.h but not exported"
     L.cq_abi_version.restype = ctypes.c_int
-    assert L.cq_abi_version() == 1
+    assert L.cq_abi_version() == 2  # 2: cq_csr.peer_row0 / peer_rowstart, cq_ipc_*
     assert set(_lib._SIGNATURES) == set(declared_symbols())
 
 
