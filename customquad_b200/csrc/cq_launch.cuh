@@ -142,6 +142,9 @@ struct StagedShape {
 #ifndef CQ_MOMENT_G3    // Q1 hexahedra: lanes per entry in the point loop, moment warps, expansion warp sets
 #define CQ_MOMENT_G3 2
 #endif
+#ifndef CQ_MOMENT_NPW3   // stage slots (= producer warps)
+#define CQ_MOMENT_NPW3 4
+#endif
 #ifndef CQ_MOMENT_NMW3
 #define CQ_MOMENT_NMW3 4
 #endif
@@ -193,7 +196,7 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
     // ... and on Q1 hexahedra (create_box meshes): 27 moments, two expansion roles
     if constexpr (T::DIM == 3 && T::DEG == 1 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {
       if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3)
-        return launch_moment_split<T, CQ_MOMENT_G3, 4, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
+        return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
     }
     return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
   }
