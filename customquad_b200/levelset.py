@@ -19,6 +19,13 @@ outputs and conventions as ``generate_qr`` (algoim_utils.py:169-180):
 * weights divided by the cell volume (algoim_utils.hpp:127-132) and points mapped to the unit
   cell (x - xmin)/dx (algoim_utils.hpp:134-143).
 
+The sphere (``demo/sphere.hpp:14-34``, ``generate_qr_sphere``) is sliced along one axis: every
+cross-section of ball ∩ cell is a disk ∩ rectangle, for which the 2-D rules above apply; the
+slicing variable is integrated with Gauss points between the heights where the cross-section
+changes type (the circle passes a corner of the rectangle or touches an edge, or the ball ends),
+after a smooth-step change of variable that removes the square-root end-point behaviour at the
+tangencies.  The surface rule uses the hat-box identity dS = R dtheta du.
+
 Host numpy code: it runs once per mesh before the timed path, like the reference's generator.
 """
 from __future__ import annotations
@@ -84,18 +91,29 @@ def _surface_rule_cell(lo, hi, c, R, n1):
                         xy = np.empty(2)
                         xy[d], xy[1 - d] = edge, o
                         ang.append(np.arctan2(xy[1], xy[0]))
+    inside = lambda p: bool(np.all(p >= lo - 1e-13) and np.all(p <= hi + 1e-13))  # noqa: E731
+    arcs = []
     if len(ang) < 2:
-        return np.zeros((0, 2)), np.zeros(0), np.zeros((0, 2))
-    ang = np.unique(np.round(np.sort(np.asarray(ang)), 14))
+        # no crossing: the whole circle is inside the cell (small cross-sections near the poles of a sphere) or outside
+        if inside(c + np.array([R, 0.0])) and inside(c - np.array([R, 0.0])) and inside(c + np.array([0.0, R])) and inside(c - np.array([0.0, R])):
+            arcs = [(0.0, 2 * np.pi)]
+    else:
+        ang = np.unique(np.round(np.sort(np.asarray(ang)), 14))
+        m = len(ang)
+        for k in range(m):
+            th0 = ang[k]
+            th1 = ang[(k + 1) % m] + (2 * np.pi if k == m - 1 else 0.0)
+            if th1 - th0 < 1e-13:
+                continue
+            mid = 0.5 * (th0 + th1)
+            if inside(c + R * np.array([np.cos(mid), np.sin(mid)])):
+                arcs.append((th0, th1))
     g, gw = _gauss01(n1)
     P, W, Nn = [], [], []
-    m = len(ang)
-    for k in range(m):
-        th0 = ang[k]
-        th1 = ang[(k + 1) % m] + (2 * np.pi if k == m - 1 else 0.0)
-        mid = 0.5 * (th0 + th1)
-        pm = c + R * np.array([np.cos(mid), np.sin(mid)])
-        if np.all(pm >= lo - 1e-13) and np.all(pm <= hi + 1e-13) and th1 - th0 < np.pi:  # arc inside the cell
+    for a0, a1 in arcs:
+        pieces = max(1, int(np.ceil((a1 - a0) / (0.5 * np.pi))))  # Gauss on arcs of at most a quarter turn
+        for j in range(pieces):
+            th0, th1 = a0 + (a1 - a0) * j / pieces, a0 + (a1 - a0) * (j + 1) / pieces
             th = th0 + (th1 - th0) * g
             n = np.stack([np.cos(th), np.sin(th)], axis=1)
             P.append(c + R * n)
@@ -104,6 +122,107 @@ def _surface_rule_cell(lo, hi, c, R, n1):
     if not P:
         return np.zeros((0, 2)), np.zeros(0), np.zeros((0, 2))
     return np.concatenate(P), np.concatenate(W), np.concatenate(Nn)
+
+
+def _slice_nodes(lo_u, hi_u, brk, n1):
+    """Gauss nodes / weights in u on [lo_u, hi_u] split at `brk`, each piece mapped by the smooth step
+    u = a + (b - a) x^2 (3 - 2x): du vanishes at both ends, which turns sqrt(u - a) type integrands
+    (a cross-section appearing through a tangency) into smooth ones."""
+    pts = sorted({lo_u, hi_u, *[b for b in brk if lo_u < b < hi_u]})
+    g, gw = _gauss01(n1)
+    U, W = [], []
+    for a, b in zip(pts[:-1], pts[1:]):
+        if b - a < 1e-13 * max(1.0, abs(a)):
+            continue
+        U.append(a + (b - a) * g * g * (3.0 - 2.0 * g))
+        W.append((b - a) * 6.0 * g * (1.0 - g) * gw)
+    if not U:
+        return np.zeros(0), np.zeros(0)
+    return np.concatenate(U), np.concatenate(W)
+
+
+def _sphere_rules_cell(lo, hi, c, R, n1, axis):
+    """Bulk (points, weights) and surface (points, weights, unit normals) rules of [lo, hi] ∩ ball(c, R),
+    sliced along `axis`."""
+    st = [d for d in range(3) if d != axis]
+    u0, u1 = max(lo[axis] - c[axis], -R), min(hi[axis] - c[axis], R)
+    if u1 <= u0:
+        return (np.zeros((0, 3)), np.zeros(0)), (np.zeros((0, 3)), np.zeros(0), np.zeros((0, 3)))
+    lo2, hi2, c2 = lo[st], hi[st], c[st]
+    # heights where the cross-section circle (radius sqrt(R^2 - u^2)) passes a corner or touches an edge line
+    brk = []
+    rel = [np.array([lo2[0] - c2[0], hi2[0] - c2[0]]), np.array([lo2[1] - c2[1], hi2[1] - c2[1]])]
+    for a in rel[0]:
+        for b in rel[1]:
+            d2 = R * R - a * a - b * b
+            if d2 > 0:
+                brk += [-np.sqrt(d2), np.sqrt(d2)]
+    for k in (0, 1):
+        for a in rel[k]:
+            d2 = R * R - a * a
+            if d2 > 0 and rel[1 - k][0] <= 0.0 <= rel[1 - k][1]:
+                brk += [-np.sqrt(d2), np.sqrt(d2)]
+    n_u = n1 + 2  # the change of variable costs a little accuracy on smooth pieces
+    U, WU = _slice_nodes(u0, u1, brk, n_u)
+    Pb, Wb, Ps, Ws, Ns = [], [], [], [], []
+    for u, wu in zip(U, WU):
+        rho2 = R * R - u * u
+        if rho2 <= 0:
+            continue
+        rho = np.sqrt(rho2)
+        p2, w2 = _bulk_rule_cell(lo2, hi2, c2, rho, n1)
+        if w2.size:
+            p = np.empty((w2.size, 3))
+            p[:, st] = p2
+            p[:, axis] = u + c[axis]
+            Pb.append(p)
+            Wb.append(w2 * wu)
+        q2, wq, nq = _surface_rule_cell(lo2, hi2, c2, rho, n1)
+        if wq.size:
+            p = np.empty((wq.size, 3))
+            p[:, st] = q2
+            p[:, axis] = u + c[axis]
+            Ps.append(p)
+            Ws.append(wq / rho * R * wu)  # arc length rho dtheta -> dtheta; dS = R dtheta du
+            Ns.append((p - c) / R)
+    cat = lambda L, shape: np.concatenate(L) if L else np.zeros(shape)  # noqa: E731
+    return (cat(Pb, (0, 3)), cat(Wb, 0)), (cat(Ps, (0, 3)), cat(Ws, 0), cat(Ns, (0, 3)))
+
+
+def generate_qr_sphere(mesh, radius=1.0, center=(0.0, 0.0, 0.0), order=4, axis=2):
+    """``generate_qr(mesh, NN, degree, "sphere", opts)`` (demo/algoim_utils.py:92-180, demo/sphere.hpp):
+    same outputs and conventions as generate_qr_circle, for hexahedral meshes."""
+    assert mesh.topology.dim == 3, "sphere: 3-D meshes"
+    nx, ny, nz = mesh.shape
+    h = mesh.h()
+    c = np.asarray(center, dtype=np.float64)
+    R = float(radius)
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ix, iy, iz = ix.reshape(-1), iy.reshape(-1), iz.reshape(-1)  # cell = (iz * ny + iy) * nx + ix (Mesh.cell_index)
+    lo = np.stack([mesh.xmin[0] + ix * h[0], mesh.xmin[1] + iy * h[1], mesh.xmin[2] + iz * h[2]], axis=1)
+    hi = lo + h[None, :]
+    near = np.clip(c[None, :], lo, hi) - c[None, :]
+    far = np.maximum(np.abs(lo - c[None, :]), np.abs(hi - c[None, :]))
+    rmin2, rmax2 = np.sum(near * near, axis=1), np.sum(far * far, axis=1)
+    outside = rmin2 >= R * R
+    uncut = rmax2 <= R * R
+    cut_cells = np.nonzero(~(outside | uncut))[0].astype(np.int32)
+    vol = float(np.prod(h))
+    n1 = max(2, (order + 2) // 2)
+    keep, qr_pts, qr_w, qr_pts_b, qr_w_b, qr_n = [], [], [], [], [], []
+    for cell in cut_cells:
+        (p, w), (pb, wb, nb) = _sphere_rules_cell(lo[cell], hi[cell], c, R, n1, axis)
+        if w.size == 0 or w.sum() < 1e-14 * vol:
+            outside[cell] = True
+            continue
+        keep.append(cell)
+        qr_pts.append(((p - lo[cell]) / h).reshape(-1))
+        qr_w.append(w / vol)
+        qr_pts_b.append(((pb - lo[cell]) / h).reshape(-1))
+        qr_w_b.append(wb / vol)
+        qr_n.append(nb.reshape(-1))
+    return (np.asarray(keep, dtype=np.int32), np.nonzero(uncut)[0].astype(np.int32), np.nonzero(outside)[0].astype(np.int32),
+            qr_pts, qr_w, qr_pts_b, qr_w_b, qr_n)  # fmt: skip
 
 
 def generate_qr_circle(mesh, radius=1.0, center=(0.0, 0.0), order=4):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""CutFEM Poisson on the unit circle, Q1 quadrilaterals: the reference's demo/poisson.py
-(BASELINE.json configs[0]) on this package.
+"""CutFEM Poisson on the unit circle (Q1 quadrilaterals) or the unit sphere (Q1 hexahedra): the
+reference's demo/poisson.py (BASELINE.json configs[0]; -domain sphere is the small version of configs[2])
+on this package.
 
 Same steps as the demo: cut-cell quadrature for the level set (here customquad_b200.levelset instead
 of Algoim, demo/poisson.py:88-113), bulk stiffness + load on the uncut cells with a standard Gauss
@@ -21,19 +22,28 @@ import numpy as np
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import customquad_b200 as cq  # noqa: E402
 from customquad_b200 import cutfem, forms, utils  # noqa: E402
-from customquad_b200.levelset import generate_qr_circle  # noqa: E402
+from customquad_b200.levelset import generate_qr_circle, generate_qr_sphere  # noqa: E402
 
 
-def solve(N, betaN=10.0, betas=1.0, order=4):
+def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle"):
     import scipy.sparse.linalg as spla
 
-    xmin, xmax = np.array([-1.11, -1.51]), np.array([1.55, 1.22])  # demo/poisson.py:40-41
-    mesh = cq.create_rectangle([xmin, xmax], [N, N])
-    cut_cells, uncut_cells, outside_cells, qr_pts, qr_w, qr_pts_bdry, qr_w_bdry, qr_n = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
+    if domain == "circle":  # demo/poisson.py:39-50
+        xmin, xmax = np.array([-1.11, -1.51]), np.array([1.55, 1.22])
+        volume_exact, area_exact = np.pi, 2 * np.pi
+        mesh = cq.create_rectangle([xmin, xmax], [N, N])
+        rules = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
+    else:
+        xmin, xmax = np.array([-1.11, -1.51, -1.23]), np.array([1.55, 1.22, 1.11])
+        volume_exact, area_exact = 4 * np.pi / 3, 4 * np.pi
+        mesh = cq.create_box([xmin, xmax], [N, N, N])
+        rules = generate_qr_sphere(mesh, 1.0, (0.0, 0.0, 0.0), order)
+    gdim = len(xmin)
+    cut_cells, uncut_cells, outside_cells, qr_pts, qr_w, qr_pts_bdry, qr_w_bdry, qr_n = rules
     V = cq.FunctionSpace(mesh, ("Lagrange", 1))
-    u_ex = cq.Analytic.sinprod(1.0)  # sin(pi x) sin(pi y)  (:59-67)
-    f = cq.Analytic.sinprod(2 * np.pi**2)  # -div grad u_ex  (:147)
-    g = cq.Function(V).interpolate(lambda x: np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]))  # (:146)
+    u_ex = cq.Analytic.sinprod(1.0)  # prod_d sin(pi x_d)  (:59-67)
+    f = cq.Analytic.sinprod(gdim * np.pi**2)  # -div grad u_ex  (:147)
+    g = cq.Function(V).interpolate(lambda x: np.prod(np.sin(np.pi * x[:gdim]), axis=0))  # (:146)
 
     qr_uncut = cutfem.standard_rule(mesh, uncut_cells, 2)  # dx_uncut: dolfinx's default degree for Q1 x Q1 gradients
     qr_bulk = [(cut_cells, qr_pts, qr_w)]
@@ -72,11 +82,11 @@ def solve(N, betaN=10.0, betas=1.0, order=4):
     area_func = cq.assemble_scalar(forms.integral(mesh, 1.0), qr_bdry)
     volume_func = assemble(lambda: forms.integral(mesh, 1.0))
     return {
-        "N": N, "h": float(np.max(mesh.h())), "cut_cells": int(len(cut_cells)), "uncut_cells": int(len(uncut_cells)),
+        "domain": domain, "N": N, "h": float(np.max(mesh.h())), "cut_cells": int(len(cut_cells)), "uncut_cells": int(len(uncut_cells)),
         "L2_err": float(L2), "H10_err": float(H10),
-        "functional_volume_err": abs(volume_func - np.pi) / np.pi, "functional_area_err": abs(area_func - 2 * np.pi) / (2 * np.pi),
-        "qr_volume_err": abs(utils.volume(xmin, xmax, [N, N], uncut_cells, qr_w) - np.pi) / np.pi,
-        "qr_area_err": abs(utils.area(xmin, xmax, [N, N], qr_w_bdry) - 2 * np.pi) / (2 * np.pi),
+        "functional_volume_err": abs(volume_func - volume_exact) / volume_exact, "functional_area_err": abs(area_func - area_exact) / area_exact,
+        "qr_volume_err": abs(utils.volume(xmin, xmax, [N] * gdim, uncut_cells, qr_w) - volume_exact) / volume_exact,
+        "qr_area_err": abs(utils.area(xmin, xmax, [N] * gdim, qr_w_bdry) - area_exact) / area_exact,
     }  # fmt: skip
 
 
@@ -85,5 +95,6 @@ if __name__ == "__main__":
     ap.add_argument("-N", type=int, default=32)  # demo/poisson.py:13
     ap.add_argument("-betaN", type=float, default=10.0)
     ap.add_argument("-betas", type=float, default=1.0)
+    ap.add_argument("-domain", default="circle", choices=["circle", "sphere"])  # demo/poisson.py:17
     a = ap.parse_args()
-    print(json.dumps(solve(a.N, a.betaN, a.betas)))
+    print(json.dumps(solve(a.N, a.betaN, a.betas, domain=a.domain)))

@@ -28,3 +28,22 @@ def test_poisson_circle_converges(cuda_backend):
     assert min(rate_l2) > 1.7, (l2, rate_l2)  # O(h^2)
     assert min(rate_h1) > 0.85, (h1, rate_h1)  # O(h)
     assert l2[-1] < 5e-3 and h1[-1] < 0.25  # measured: 3.07e-3, 0.175 at N = 64
+
+
+def test_poisson_sphere_converges(cuda_backend):
+    """-domain sphere (demo/poisson.py:45-49): Q1 hexahedra -- the 27-moment mass / stiffness kernel, the 4-set
+    Nitsche moment kernel with quadrature normals, hex load vectors and functionals -- in the demo's own setting."""
+    import poisson
+
+    res = [poisson.solve(N, domain="sphere") for N in (8, 16, 24)]
+    for r in res:
+        assert r["functional_area_err"] < 1e-4 and r["functional_volume_err"] < 1e-4
+        assert abs(r["functional_volume_err"] - r["qr_volume_err"]) < 1e-12
+        assert abs(r["functional_area_err"] - r["qr_area_err"]) < 1e-12
+    l2 = [r["L2_err"] for r in res]
+    h1 = [r["H10_err"] for r in res]
+    hs = [r["h"] for r in res]
+    rate_l2 = [np.log(l2[i] / l2[i + 1]) / np.log(hs[i] / hs[i + 1]) for i in range(2)]
+    rate_h1 = [np.log(h1[i] / h1[i + 1]) / np.log(hs[i] / hs[i + 1]) for i in range(2)]
+    assert min(rate_l2) > 1.6, (l2, rate_l2)
+    assert min(rate_h1) > 0.8, (h1, rate_h1)

@@ -32,6 +32,30 @@ def test_circle_rules_volume_area_and_conventions():
     assert errs[0] < 1e-4 and errs[1] < errs[0] / 20 and errs[2] < errs[1] / 20  # high-order convergence of the bulk rules
 
 
+def test_sphere_rules_volume_area_and_conventions():
+    from customquad_b200.levelset import generate_qr_sphere
+
+    xmin, xmax = np.array([-1.11, -1.51, -1.23]), np.array([1.55, 1.22, 1.11])  # demo/poisson.py:46-47
+    errs = []
+    for N in (6, 12):
+        mesh = cq.create_box([xmin, xmax], [N, N, N])
+        cut, uncut, outside, qp, qw, qpb, qwb, qn = generate_qr_sphere(mesh, 1.0, (0.0, 0.0, 0.0), order=4)
+        assert len(cut) + len(uncut) + len(outside) == mesh.num_cells
+        h = mesh.h()
+        for cell, p, w, pb, wb, n in zip(cut, qp, qw, qpb, qwb, qn):
+            assert p.size == 3 * w.size and pb.size == 3 * wb.size == n.size
+            assert np.all(w > 0) and w.sum() < 1.0 + 1e-10 and np.all(wb > 0)
+            assert np.all((p > -1e-12) & (p < 1 + 1e-12)) and np.all((pb > -1e-12) & (pb < 1 + 1e-12))
+            iz, rem = divmod(int(cell), N * N)
+            iy, ix = divmod(rem, N)
+            x = xmin + np.array([ix, iy, iz]) * h + pb.reshape(-1, 3) * h
+            assert np.allclose(np.linalg.norm(x, axis=1), 1.0) and np.allclose(x, n.reshape(-1, 3))  # on the sphere, radial unit normal
+        vol = utils.volume(xmin, xmax, [N, N, N], uncut, qw)
+        area = utils.area(xmin, xmax, [N, N, N], qwb)
+        errs.append((abs(vol - 4 * np.pi / 3) / (4 * np.pi / 3), abs(area - 4 * np.pi) / (4 * np.pi)))
+    assert errs[0][0] < 1e-4 and errs[0][1] < 1e-4 and errs[1][0] < 1e-5 and errs[1][1] < 1e-5, errs
+
+
 def test_surface_points_on_circle():
     N = 12
     mesh = cq.create_rectangle([XMIN, XMAX], [N, N])
