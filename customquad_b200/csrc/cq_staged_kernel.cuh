@@ -4,6 +4,10 @@
 #include "cq_moment.cuh"
 #include "cq_staged.cuh"
 
+#ifndef CQ_POS_BULK_MIN  // scatter maps of at least this many bytes per cell travel by cp.async.bulk
+#define CQ_POS_BULK_MIN 64
+#endif
+
 namespace cq {
 
 // ---- producer role (one warp per stage slot) ----------------------------------------------------------
@@ -27,7 +31,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
     double* s_pts = reinterpret_cast<double*>(base + Lay::meta_bytes);
     double* s_w = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB));
     double* s_nrm = reinterpret_cast<double*>(base + Lay::meta_bytes + Lay::pts_bytes(PB) + Lay::w_bytes(PB));
-    constexpr bool POS_BULK = Meta::MAT && Meta::NPOS > 64;  // larger maps: bulk copy instead of registers
+    constexpr bool POS_BULK = Meta::MAT && Meta::NPOS >= CQ_POS_BULK_MIN;  // larger maps: bulk copy instead of registers
     constexpr int NP16 = (Meta::MAT && !POS_BULK) ? Meta::NPOS / 16 : 1;
     struct Regs {
       long long t;  // stage index; -2: pipeline bubble, -1: no more work
