@@ -2,6 +2,17 @@
 #include "cq_dmma.cuh"
 #include "cq_launch.cuh"
 
+// consumer warps (one entry per warp) of the staged Q2-hexahedron tensor-core kernel.  Measured on 48^3 cells with 27
+// points each (profiles/r1/q2hex_ncw.txt): scalar spaces are bound by the contraction and gain from 13 warps
+// (stiffness 2.19 -> 1.45 ms), blocked spaces (bs = 3, 9x the scatter per entry) are bound by the RED scatter and are
+// fastest with 5 (3.52 ms; 3.89 ms with 13).
+#ifndef CQ_DMMA_NCW
+#define CQ_DMMA_NCW 13
+#endif
+#ifndef CQ_DMMA_NCW_BLOCKED
+#define CQ_DMMA_NCW_BLOCKED 5
+#endif
+
 namespace cq {
 
 template <int FORM>
@@ -21,7 +32,11 @@ static int launch_matrix_form(cq_ctx* ctx, const cq_form_desc& f, const KParams&
   if (!quad && f.degree == 1) return launch_auto<FormTraits<FORM, 3, 1, 1, CQ_FN_CONST>>(ctx, P, s);
   // Q2 hexahedron: FP64 tensor-core contraction, staged (warp per entry) when the scatter map is there
   using TQ2 = FormTraits<FORM, 3, 2, 1, CQ_FN_CONST>;
-  if (staged_ok<TQ2>(ctx, P)) return launch_staged<TQ2, 32, TQ2::NEED_NORMAL ? 2 : 3, 5, 2>(ctx, P, s);
+  if (staged_ok<TQ2>(ctx, P)) {
+    constexpr int NPW = TQ2::NEED_NORMAL ? 2 : 3;
+    return P.bs == 1 ? launch_staged<TQ2, 32, NPW, CQ_DMMA_NCW, 2>(ctx, P, s)
+                     : launch_staged<TQ2, 32, NPW, CQ_DMMA_NCW_BLOCKED, 2>(ctx, P, s);
+  }
   if (ctx->variant == 2) { set_error("staged kernel requested but not applicable"); return CQ_ERR_UNSUPPORTED; }
   return launch_dmma<FORM>(ctx, P, s);
 }
