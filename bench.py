@@ -230,10 +230,12 @@ def run_gpu(args):
             A = mats[name]
             if events is not None:
                 events[i][0].record()
-            A.data.zero_()  # A.zeroEntries() (assemble_matrix.py:20)
             if fused:
+                A.data.zero_()  # A.zeroEntries() (assemble_matrix.py:20)
                 exch[name].fence(dev)  # the neighbour's kernel adds into this matrix: it must be zeroed first
-            asm.assemble_matrix(form, [qr], A=A)
+                asm.assemble_matrix(form, [qr], A=A)
+            else:
+                asm.assemble_matrix(form, [qr], A=A, zero=True)  # A.zeroEntries() + assembly in one call (cq_assemble_matrix_zero)
             if exch is not None:
                 exch[name].exchange_matrix(A.data)  # fused: only the completion fence
             if events is not None:

@@ -58,7 +58,9 @@ _SIGNATURES = {
     "cq_ctx_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cq_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "cq_ctx_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
+    "cq_ctx_set_fused_zero": (C.c_int, [C.c_void_p, C.c_int]),
     "cq_assemble_matrix": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p]),
+    "cq_assemble_matrix_zero": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p]),
     "cq_assemble_vector": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_mesh_classify": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(MeshDesc), C.POINTER(C.c_int32), C.c_void_p]),

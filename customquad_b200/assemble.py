@@ -160,13 +160,20 @@ class _Call:
         return None if self.space is None else C.byref(self.space)
 
 
-def create_matrix(form: Form, pattern_cells=None) -> CSRMatrix:
-    """Zeroed matrix on the form's pattern (create_matrix + zeroEntries, assemble_matrix.py:19-20)."""
+def set_fused_zero(on: bool) -> None:
+    """Switches the in-kernel zeroEntries of ``assemble_matrix(..., zero=True)`` on or off for this device
+    (cq_ctx_set_fused_zero; off by default, see include/cq_b200.h)."""
+    _lib.check(_lib.load().cq_ctx_set_fused_zero(_lib.ctx(_dev().index), int(bool(on))))
+
+
+def create_matrix(form: Form, pattern_cells=None, zero: bool = True) -> CSRMatrix:
+    """Zeroed matrix on the form's pattern (create_matrix + zeroEntries, assemble_matrix.py:19-20).
+    ``zero=False`` leaves the values uninitialised for ``assemble_matrix(..., zero=True)``."""
     torch = _torch()
     dev = _dev()
     V = form.function_spaces[0]
     indptr, indices = pattern_on_device(V, dev, pattern_cells)
-    data = torch.zeros(indices.shape[0], dtype=torch.float64, device=dev)
+    data = (torch.zeros if zero else torch.empty)(indices.shape[0], dtype=torch.float64, device=dev)
     n = V.num_dofs
     A = CSRMatrix(indptr, indices, data, (n, n), dev.index, _stream_ptr())
     A.full_pattern = pattern_cells is None
@@ -178,9 +185,12 @@ def _csr_desc(A: CSRMatrix):
                         getattr(A, "peer_row0", None), _ptr(getattr(A, "peer_rowstart", None)))
 
 
-def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: str = "form") -> CSRMatrix:
+def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: str = "form", zero: bool | None = None) -> CSRMatrix:
     """reference customquad/assemble_matrix.py:10-47.  Returns the (device) CSR matrix; like the
-    reference's PETSc Mat it is "unassembled" until ``A.assemble()``."""
+    reference's PETSc Mat it is "unassembled" until ``A.assemble()``.
+
+    ``zero``: A.zeroEntries() (:20) as part of the call -- the first integral runs cq_assemble_matrix_zero, which
+    zeroes inside the assembly kernel.  Default: True for a matrix created here, False (accumulate) for a given A."""
     assert form.rank == 2
     L = _lib.load()
     dev = _dev()
@@ -190,11 +200,15 @@ def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: st
         cells = None
         if pattern == "cells":
             cells = np.concatenate([np.asarray(normalise_qr(qr_data[i], form.mesh.geometry.dim).cells) for i in range(len(ids))])
-        A = create_matrix(form, cells)
+        zero = True if zero is None else zero
+        A = create_matrix(form, cells, zero=not zero)
     csr = _csr_desc(A)
+    if zero and not ids:
+        A.data.zero_()
     for i, _id in enumerate(ids):  # qr tuples are matched to integrals by position (:26,42)
         c = _Call(form, qr_data[i], dev, A=A)
-        _lib.check(L.cq_assemble_matrix(ctx, C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), _stream_ptr()))
+        fn = L.cq_assemble_matrix_zero if (zero and i == 0) else L.cq_assemble_matrix
+        _lib.check(fn(ctx, C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), _stream_ptr()))
     A.assembled = False
     return A
 

@@ -1,5 +1,6 @@
 // cq_api.cu -- the C-ABI of libcq_b200.so (include/cq_b200.h): argument checking, context,
 // parameter packing, and the host-buffer (end-to-end) entry points.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -215,6 +216,8 @@ int cq_ctx_create(int device, cq_ctx** out) {
   if (!c) { set_error("out of host memory"); return CQ_ERR_INVALID; }
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  c->coop_launch = prop.cooperativeLaunch;
+  c->fused_zero = getenv("CQ_ZERO_FUSED") ? atoi(getenv("CQ_ZERO_FUSED")) != 0 : 0;
   int rc = check_cuda(cudaMalloc(&c->err_flag, sizeof(int)), "cudaMalloc(err_flag)");
   if (!rc) rc = check_cuda(cudaMemset(c->err_flag, 0, sizeof(int)), "cudaMemset(err_flag)");
   if (!rc) rc = check_cuda(cudaMalloc(&c->work_counter, sizeof(unsigned int)), "cudaMalloc(work_counter)");
@@ -239,6 +242,7 @@ int cq_ctx_destroy(cq_ctx* ctx) {
   if (ctx->work_counter) cudaFree(ctx->work_counter);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->scalar_dev) cudaFree(ctx->scalar_dev);
+  if (ctx->zero_buf) cudaFree(ctx->zero_buf);
   if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->kev) if (e) cudaEventDestroy(e);
@@ -273,15 +277,18 @@ int cq_ctx_set_variant(cq_ctx* ctx, int variant) {
   return CQ_OK;
 }
 
-int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
-                       const cq_quadrature* qr, const cq_csr* A, void* stream) {
+static int assemble_matrix_impl(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                                const cq_quadrature* qr, const cq_csr* A, void* stream, const bool zero_first) {
   KParams P;
   if (int rc = pack(ctx, form, mesh, space, qr, P)) return rc;
   if (rank_of(form->form) != 2) { set_error("form %d is not a bilinear form", form->form); return CQ_ERR_INVALID; }
   if (!A || !A->indptr || !A->indices || !A->values) { set_error("CSR arrays null"); return CQ_ERR_INVALID; }
   if (A->num_rows != space->num_dofs * form->bs) { set_error("CSR rows %lld != num_dofs*bs %lld", (long long)A->num_rows, (long long)(space->num_dofs * form->bs)); return CQ_ERR_INVALID; }
-  if (qr->num_entries == 0) return CQ_OK;
   if (int rc = set_device(ctx)) return rc;
+  if (qr->num_entries == 0)
+    return zero_first ? check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * (size_t)A->nnz, static_cast<cudaStream_t>(stream)), "zeroEntries") : CQ_OK;
+  P.zero_req = zero_first ? 1 : 0;
+  P.nnz = A->nnz;
   P.indptr = A->indptr; P.indices = A->indices; P.values = A->values;
   if (A->peer_rowstart) {
     if (A->peer_row0 < 0 || A->peer_row0 > A->num_rows) { set_error("peer_row0 out of range"); return CQ_ERR_INVALID; }
@@ -290,6 +297,22 @@ int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
     P.peer_rowstart = reinterpret_cast<const long long*>(A->peer_rowstart);
   }
   return launch_matrix(ctx, *form, P, static_cast<cudaStream_t>(stream));
+}
+
+int cq_ctx_set_fused_zero(cq_ctx* ctx, int on) {
+  if (!ctx) { set_error("null ctx"); return CQ_ERR_INVALID; }
+  ctx->fused_zero = on != 0;
+  return CQ_OK;
+}
+
+int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                       const cq_quadrature* qr, const cq_csr* A, void* stream) {
+  return assemble_matrix_impl(ctx, form, mesh, space, qr, A, stream, false);
+}
+
+int cq_assemble_matrix_zero(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                            const cq_quadrature* qr, const cq_csr* A, void* stream) {
+  return assemble_matrix_impl(ctx, form, mesh, space, qr, A, stream, true);
 }
 
 int cq_assemble_vector(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,

@@ -28,6 +28,11 @@ struct cq_ctx {
   size_t stage_bytes = 0;
   int* host_flag = nullptr;  // pinned
   double* scalar_dev = nullptr;  // device accumulator of the host-buffer scalar path
+  // fused zeroing (cq_zero.cuh): per-wave value ranges + completion counters, grow-only
+  int coop_launch = 0;  // device supports cooperative launches
+  int fused_zero = 0;   // cq_ctx_set_fused_zero
+  void* zero_buf = nullptr;
+  size_t zero_waves = 0;
 };
 
 namespace cq {

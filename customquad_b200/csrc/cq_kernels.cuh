@@ -40,6 +40,13 @@ struct KParams {
   int dbg;                               // profiling experiments only (CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)
   int elem_out;    // 1: write un-scattered element tensors to out[k, :]
+  // fused A.zeroEntries() (cq_assemble_matrix_zero, cq_zero.cuh): the kernel itself zeroes `values` just ahead of
+  // the scatter, so the REDs hit zeroed lines that are still in L2 instead of reading a memset's lines back from HBM
+  int zero_req;                          // 1: values are uninitialised, zero them (in the kernel, or by a memset)
+  int zero_ahead;                        // waves zeroed ahead of the scatter
+  long long nnz;
+  const long long* __restrict__ zero_hi; // [waves] values[0 .. zero_hi[k]) covers every slot the waves <= k touch; null: no fused zeroing
+  unsigned int* zero_done;               // [waves] warps that have finished zeroing their part of wave k's range
   double betaN;
   double p[CQ_MAX_CONSTS];
 };

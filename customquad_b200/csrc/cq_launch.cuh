@@ -8,8 +8,49 @@
 
 namespace cq {
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- fused zeroEntries (cq_zero.cuh) ----------------------------------------------------------------
+// Sets P.zero_hi / zero_done / zero_ahead for a launch of `grid` CTAs (stream-ordered).  The caller has checked that
+// the kernel supports it; on return P.zero_req is cleared.
+static int prepare_fused_zero(cq_ctx* ctx, KParams& P, const int n, const int grid, cudaStream_t s) {
+  const int64_t num_stages = (P.num_entries + 31) / 32;
+  const int64_t waves = (num_stages + grid - 1) / grid;
+  if ((size_t)waves > ctx->zero_waves) {
+    if (ctx->zero_buf) cudaFree(ctx->zero_buf);
+    ctx->zero_buf = nullptr;
+    ctx->zero_waves = 0;
+    const size_t cap = (size_t)waves + (size_t)waves / 4 + 64;
+    if (int rc = check_cuda(cudaMalloc(&ctx->zero_buf, cap * 12), "cudaMalloc(zero ranges)")) return rc;
+    ctx->zero_waves = cap;
+  }
+  unsigned long long* raw = static_cast<unsigned long long*>(ctx->zero_buf);
+  unsigned int* done = reinterpret_cast<unsigned int*>(raw + ctx->zero_waves);
+  if (int rc = check_cuda(cudaMemsetAsync(done, 0, (size_t)waves * 4, s), "memset(zero_done)")) return rc;
+  const int64_t blocks = waves < (int64_t)ctx->num_sms * 16 ? waves : (int64_t)ctx->num_sms * 16;
+  wave_hi_kernel<><<<(int)blocks, 256, 0, s>>>(P.cells, P.num_entries, P.dofmap, n, P.bs, P.indptr, P.nnz, grid, raw);
+  wave_scan_kernel<><<<1, 1024, 0, s>>>(raw, waves);
+  ctx->launches += 2;
+  if (int rc = check_cuda(cudaGetLastError(), "fused-zero setup kernels")) return rc;
+  static const int ahead = getenv("CQ_ZERO_AHEAD") ? atoi(getenv("CQ_ZERO_AHEAD")) : 6;
+  P.zero_hi = reinterpret_cast<const long long*>(raw);
+  P.zero_done = done;
+  P.zero_ahead = ahead < 4 ? 4 : ahead;  // at least the batch of the zeroing warp (no deadlock: cq_staged_kernel.cuh)
+  P.zero_req = 0;
+  return CQ_OK;
+}
+
+// kernels without the fused zeroing: a memset does it
+static int prezero(KParams& P, cudaStream_t s) {
+  if (!P.zero_req) return CQ_OK;
+  P.zero_req = 0;
+  return check_cuda(cudaMemsetAsync(P.values, 0, sizeof(double) * (size_t)P.nnz, s), "zeroEntries");
+}
+
+
 template <class T, int G>
-static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
+static int launch_direct(cq_ctx* ctx, KParams P, cudaStream_t s) {
+  if (int rc = prezero(P, s)) return rc;
   constexpr int THREADS = 256;
   constexpr int64_t ENTRIES_PER_BLOCK = (THREADS / 32) * (32 / G);
   const int grid = grid_for<assemble_direct_kernel<T, G, THREADS>>(ctx, THREADS, ENTRIES_PER_BLOCK, P.num_entries);
@@ -17,8 +58,6 @@ static int launch_direct(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "assemble_direct_kernel launch");
 }
-
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Can this call run the staged kernel?  (Otherwise the direct kernel handles it.)
 template <class T>
@@ -31,6 +70,7 @@ static bool staged_ok(const cq_ctx* ctx, const KParams& P) {
 
 template <class T, int G, int NPW, int NCW, int MODE = 0>
 static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
+  if (int rc = prezero(P, s)) return rc;
   constexpr int CB = 32;
   using Lay = StagedLayout<T, CB>;
   auto kernel = assemble_staged_kernel<T, G, NPW, NCW, MODE>;
@@ -61,11 +101,17 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
 }
 
-template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1>
+// Can the persistent moment kernels zero the matrix themselves (cq_zero.cuh)?  Not with peer rows: the neighbour's
+// kernel adds into this matrix at any time.
+static bool fused_zero_ok(const cq_ctx* ctx, const KParams& P) {
+  return P.zero_req && ctx->fused_zero && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
+}
+
+template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1, int ZW = 0>
 static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   constexpr int CB = 32;
   using Lay = StagedLayout<T, CB>;
-  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW, XT, NPP>;
+  auto kernel = assemble_moment_split_kernel<T, G, NPW, NMW, NXW, XT, NPP, ZW>;
   const size_t budget = (size_t)ctx->max_smem_optin - 1024;
   const size_t per_point = (size_t)T::DIM * 8 * (T::NEED_NORMAL ? 2 : 1) + 8;
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
@@ -94,7 +140,18 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   }
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
-  kernel<<<grid, (NPW * NPP + NMW + NXW) * 32, smem, s>>>(P);
+  if (P.zero_req) {
+    // fused zeroEntries (cq_zero.cuh); not with peer rows (the neighbour's kernel adds into this matrix at any time)
+    if (ZW && fused_zero_ok(ctx, P)) {
+      if (int rc = prepare_fused_zero(ctx, P, T::N, grid, s)) return rc;
+      void* args[] = {(void*)&P};
+      ctx->launches++;
+      return check_cuda(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3((NPW * NPP + NMW + NXW + ZW) * 32), args, smem, s),
+                        "assemble_moment_split_kernel cooperative launch");
+    }
+    if (int rc = prezero(P, s)) return rc;
+  }
+  kernel<<<grid, (NPW * NPP + NMW + NXW + ZW) * 32, smem, s>>>(P);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "assemble_moment_split_kernel launch");
 }
@@ -180,8 +237,16 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // organisations are bound by the L2 atomic rate of the 81 REDs per cell (2.56 vs 2.59 ms)
         // split = 2: row-owned expansion + transposed scatter (RowTile, cq_moment.cuh)
         static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : 2;
-        if (split == 2) return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2), (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1), true, CQ_MOMENT_NPP>(ctx, P, s);
-        if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1>(ctx, P, s);
+        if (split == 2) {
+          // fused zeroEntries (opt-in, cq_ctx_set_fused_zero): one more warp.  Q1: 4 + 8 + 2 + 1 warps still cost 16
+          // warps' worth of registers; Q2: 4 + 6 + 6 = 16 warps at 128 registers, so the zeroing warp takes the place
+          // of a moment warp (a 17th warp costs the registers of 20: 96 per thread, spills in the point loop)
+          constexpr int NMW = T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2;
+          constexpr int NXW = (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1);
+          if (fused_zero_ok(ctx, P)) return launch_moment_split<T, CQ_MOMENT_SG, 4, NMW - (T::DEG == 2 ? 1 : 0), NXW, true, CQ_MOMENT_NPP, 1>(ctx, P, s);
+          return launch_moment_split<T, CQ_MOMENT_SG, 4, NMW, NXW, true, CQ_MOMENT_NPP, 0>(ctx, P, s);
+        }
+        if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1, false, 1, 0>(ctx, P, s);
         return launch_staged<T, CQ_MOMENT_G, CQ_MOMENT_NPW, CQ_MOMENT_NPW * CQ_MOMENT_G, 1>(ctx, P, s);
       }
     }

@@ -16,7 +16,8 @@
 namespace cq {
 
 template <int FORM>
-static int launch_dmma(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
+static int launch_dmma(cq_ctx* ctx, KParams P, cudaStream_t s) {
+  if (int rc = prezero(P, s)) return rc;
   constexpr int THREADS = 128;
   const int grid = grid_for<assemble_q2hex_dmma_kernel<FORM, THREADS>>(ctx, THREADS, THREADS / 32, P.num_entries);
   assemble_q2hex_dmma_kernel<FORM, THREADS><<<grid, THREADS, 0, s>>>(P);

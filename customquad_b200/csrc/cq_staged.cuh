@@ -57,6 +57,19 @@ CQ_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, ui
                : "memory");
 }
 
+// The same copy for data that is read exactly once (the rule's points / weights / normals, the scatter map): L2
+// evict-first, so the stream does not push the matrix lines (zeroed ahead of the scatter, cq_zero.cuh) out of the L2.
+CQ_DEVINL uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+CQ_DEVINL void bulk_g2s_once(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, const uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
 // ---- stage layout ------------------------------------------------------------------------------------
 template <class T, int CB>
 struct StageMeta {

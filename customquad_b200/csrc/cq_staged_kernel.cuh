@@ -3,6 +3,7 @@
 #include "cq_dmma.cuh"
 #include "cq_moment.cuh"
 #include "cq_staged.cuh"
+#include "cq_zero.cuh"
 
 #ifndef CQ_POS_BULK_MIN  // scatter maps of at least this many bytes per cell travel by cp.async.bulk
 #define CQ_POS_BULK_MIN 64
@@ -47,6 +48,12 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
       int rl[Meta::MAT ? N : 1];
     };
     Regs ra, rb, rc;
+#ifndef CQ_NO_EVICT_FIRST
+    const uint64_t pol = l2_policy_evict_first();
+#define CQ_BULK_ONCE(dst, src, bytes, bar) bulk_g2s_once(dst, src, bytes, bar, pol)
+#else
+#define CQ_BULK_ONCE(dst, src, bytes, bar) bulk_g2s(dst, src, bytes, bar)
+#endif
     ra.t = rb.t = rc.t = -2;
     ra.valid = rb.valid = rc.valid = false;
     // Stages are dealt out statically, interleaved over the CTAs and their slots: with hundreds of
@@ -94,9 +101,9 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           const uint32_t b_pts = (uint32_t)(cnt_copy * DIM * 8), b_w = (uint32_t)(cnt_copy * 8);
           mbar_arrive_expect_tx(full_bar_w, b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w + (POS_BULK ? (uint32_t)(nent * Meta::NPOS) : 0u));
           if (cnt_copy > 0) {
-            bulk_g2s(s_pts, P.pts + Pa * DIM, b_pts, full_bar_w);
-            bulk_g2s(s_w, P.w + Pa, b_w, full_bar_w);
-            if constexpr (T::NEED_NORMAL) bulk_g2s(s_nrm, P.normals + Pa * DIM, b_pts, full_bar_w);
+            CQ_BULK_ONCE(s_pts, P.pts + Pa * DIM, b_pts, full_bar_w);
+            CQ_BULK_ONCE(s_w, P.w + Pa, b_w, full_bar_w);
+            if constexpr (T::NEED_NORMAL) CQ_BULK_ONCE(s_nrm, P.normals + Pa * DIM, b_pts, full_bar_w);
           }
           if (tail) {
             const int64_t q = Pa + cnt - 1, l = cnt - 1;
@@ -126,9 +133,9 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
           const bool consec = false;
 #endif
           if (consec) {
-            if (lane == 0) bulk_g2s(&M.pos[0][0], P.elem_pos + (int64_t)cell0 * Meta::NPOS, CB * Meta::NPOS, full_bar_w);
+            if (lane == 0) CQ_BULK_ONCE(&M.pos[0][0], P.elem_pos + (int64_t)cell0 * Meta::NPOS, CB * Meta::NPOS, full_bar_w);
           } else if (ra.valid) {
-            bulk_g2s(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, full_bar_w);
+            CQ_BULK_ONCE(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, full_bar_w);
           }
         }
         if (ra.valid) {
@@ -363,8 +370,9 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
 // ---------------------------------------------------------------------------------------------
 // XT: row-owned expansion with the transposed scatter (RowTile, cq_moment.cuh); NXW = sets * (DEG + 1)
 // NPP: producer warps per stage slot
-template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1>
-__global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
+// ZW: 1 = one more warp that zeroes the matrix ahead of the scatter (fused zeroEntries, cq_zero.cuh)
+template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1, int ZW = 0>
+__global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
   constexpr int CB = 32;
   using Meta = StageMeta<T, CB>;
   using Lay = StagedLayout<T, CB>;
@@ -375,6 +383,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[NPW], mom_bar[NPW], empty_bar[NPW], turn_bar[NPW];
+  __shared__ volatile long long zero_progress;  // the wave the moment phase of this CTA has reached (paces the zeroing warp)
   const int PB = P.stage_points;
   const size_t stage_bytes = Lay::stage_bytes(PB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -386,12 +395,33 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
       mbar_init(&turn_bar[s], 1);
       mbar_init(&empty_bar[s], XT ? T::DEG + 1 : NXW);  // the expansion warps of one set
     }
+    zero_progress = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
 
-  if (warp < NPW * NPP) {
+  if (ZW && warp == NPW * NPP + NMW + NXW) {
+    // ------------------------------ zeroing warp (fused zeroEntries, cq_zero.cuh) ------------------------------
+    // Off every critical path: zeroes this CTA's share of the ranges of ZB waves at a time, zero_ahead waves ahead
+    // of the CTA's moment phase, then one fence and the ZB signals.
+    if (P.zero_hi == nullptr) return;
+    constexpr int ZB = 4;
+    const long long waves = (num_stages + gridDim.x - 1) / gridDim.x;
+    const int zahead = P.zero_ahead;
+    zero_share(P.values, __ldg(P.zero_hi + waves - 1), P.nnz, blockIdx.x, gridDim.x, lane);  // rows no entry touches
+    long long hi_prev = 0;
+    for (long long kz0 = 0; kz0 < waves; kz0 += ZB) {
+      const long long kz1 = kz0 + ZB < waves ? kz0 + ZB : waves;
+      const long long hi = __ldg(P.zero_hi + kz1 - 1);  // before the pacing wait: off the critical path
+      while (zero_progress < kz1 - 1 - zahead) __nanosleep(128);
+      zero_share(P.values, hi_prev, hi, blockIdx.x, gridDim.x, lane);
+      hi_prev = hi;
+      __threadfence();  // the zero stores are performed (gpu scope) before the signals
+      __syncwarp();
+      if (lane < kz1 - kz0) red_relaxed_inc_u32(P.zero_done + kz0 + lane);
+    }
+  } else if (warp < NPW * NPP) {
     const int slot = warp % NPW, sub = warp / NPW;
     // short gather (DIM + 1 coordinates per cell) where it pays: measured, Q1 quadrilaterals are faster with the
     // full gather (0.78 vs 0.86-0.94 ms), Q2 quadrilaterals (1.42 vs 1.44) and hexahedra (0.55 vs 0.78) with the short one
@@ -402,8 +432,11 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
     const int r = lane & (G - 1), grp = lane / G;
     uint32_t ended = 0, parity = 0;
     int s = 0;
+    const bool zlead = ZW && P.zero_hi != nullptr && warp == NPW * NPP && lane == 0;  // reports the progress to the zeroing warp
+    long long rnd = 0;
     while (ended != (1u << NPW) - 1u) {
       if (!((ended >> s) & 1u)) {
+        if (zlead) zero_progress = rnd * NPW + s;
         mbar_wait(&full_bar[s], parity);
         Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
         const int nent = M.nent;
@@ -426,8 +459,10 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
       if (++s == NPW) {
         s = 0;
         parity ^= 1;
+        ++rnd;
       }
     }
+    if (zlead) zero_progress = 0x7fffffffffffffffLL;
   } else {
     // ------------------------------ expansion warps ------------------------------
     // XT: warp = (set, role); role = x lattice index of the rows it owns, set k serves the stage
@@ -443,8 +478,32 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
       if (q % NXS == set) mine |= 1u << q;
     uint32_t ended = 0, parity = 0;
     int s = 0;
+    // fused zeroEntries (cq_zero.cuh): the zeroing warp zeroes the ranges zero_ahead waves ahead; here, before the
+    // scatter of wave = rnd * NPW + s, every range up to this wave's must be complete on all CTAs.  This set saw the
+    // waves <= wave - NXS complete in its previous iteration, so it looks at the counters of the last NXS waves; they
+    // are loaded one iteration ahead (normally complete long ago: the load is off the critical path).
+    const bool fz = ZW && P.zero_hi != nullptr;  // ZW == 0: all of this folds away
+    const long long waves = (num_stages + gridDim.x - 1) / gridDim.x;
+    const unsigned zexpect = gridDim.x;
+    unsigned zs[NXS];
+    auto zload = [&](const long long w) {
+#pragma unroll
+      for (int q = 0; q < NXS; ++q) {
+        const long long j = w - q;
+        zs[q] = (fz && lane == 0 && j >= 0 && j < waves) ? ld_relaxed_u32(P.zero_done + j) : zexpect;
+      }
+    };
+    auto zwait = [&](const long long w) {
+#pragma unroll
+      for (int q = 0; q < NXS; ++q)
+        while (zs[q] < zexpect) zs[q] = ld_relaxed_u32(P.zero_done + (w - q));
+      __syncwarp();
+    };
+    long long rnd = 0;
+    zload(set);
     while (ended != mine) {
       if (((mine >> s) & 1u) && !((ended >> s) & 1u)) {
+        const long long wave = rnd * NPW + s;
         mbar_wait(&mom_bar[s], parity);
         Meta& M = *reinterpret_cast<Meta*>(smem_raw + (size_t)s * stage_bytes);
         const int nent = M.nent;
@@ -459,12 +518,20 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
               static_for<0, T::DEG + 1>([&](auto RR) {
                 if (role == decltype(RR)::value) {
                   if (lane < nent) moment_expand_rows<T, CB, decltype(RR)::value>(M, lane, tile + lane * RT::STRIDE);
+                  if (fz) {
+                    zwait(wave);
+                    zload(wave + NXS);
+                  }
                   __syncwarp();
                   scatter_rows_transposed<T, CB, decltype(RR)::value>(P, M, tile, nent, lane);
                 }
               });
             }
           } else if constexpr (T::DIM == 2) {
+           if (fz) {
+             zwait(wave);
+             zload(wave + NXS);
+           }
            if (lane < nent && P.dbg != 2) {
             double mu[Pn][Pn];
 #pragma unroll
@@ -483,6 +550,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW) * 32, 1) assemble_mome
       if (++s == NPW) {
         s = 0;
         parity ^= 1;
+        ++rnd;
       }
     }
   }
