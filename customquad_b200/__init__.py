@@ -10,7 +10,7 @@ The compute path is hand-written sm_100a CUDA behind the C-ABI in include/cq_b20
 (customquad_b200/csrc); there is no CPU fallback: calling an assemble_* function without the
 built library or without a GPU raises.
 """
-from . import cutfem, fem, forms, la, levelset, mesh, quadrature, sparsity, utils  # noqa: F401
+from . import cutfem, dolfinx_adapter, fem, forms, la, levelset, mesh, quadrature, sparsity, utils  # noqa: F401
 from .assemble import assemble_matrix, assemble_scalar, assemble_vector  # noqa: F401
 from .fem import Function, FunctionSpaceQ as FunctionSpace, VectorFunctionSpace  # noqa: F401
 from .forms import Analytic  # noqa: F401
@@ -19,5 +19,5 @@ from .mesh import CellType, create_box, create_rectangle  # noqa: F401
 __all__ = [
     "assemble_matrix", "assemble_vector", "assemble_scalar",
     "create_rectangle", "create_box", "CellType", "FunctionSpace", "VectorFunctionSpace", "Function", "Analytic",
-    "forms", "fem", "mesh", "quadrature", "sparsity", "utils",
+    "forms", "fem", "mesh", "quadrature", "sparsity", "utils", "dolfinx_adapter",
 ]
