@@ -171,10 +171,15 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
 #define CQ_STAGED_NCW45 4
 #endif
 // consumer warps by accumulator size: the register file holds (NPW + NCW) * 32 threads
+// (measured, profiles/r1/configs_session3.txt: 6 slots change nothing, 8 slots cost 10-60 %)
+#ifndef CQ_STAGED_NPW_VS  // stage slots of the vector / scalar kernels with at most 16 accumulators (16 warps in all)
+#define CQ_STAGED_NPW_VS 4
+#endif
 template <class T>
 struct StagedShape {
-  static constexpr int NPW = 4;
-  static constexpr int NCW = T::NACC <= 16 ? 12 : (T::NACC <= 36 ? CQ_STAGED_NCW36 : CQ_STAGED_NCW45);
+  static constexpr bool SMALL_VS = T::RANK < 2 && T::NACC <= 16;
+  static constexpr int NPW = SMALL_VS ? CQ_STAGED_NPW_VS : 4;
+  static constexpr int NCW = T::NACC <= 16 ? 16 - NPW : (T::NACC <= 36 ? CQ_STAGED_NCW36 : CQ_STAGED_NCW45);
   static constexpr int G = T::NACC <= 16 ? 4 : (T::NACC <= 36 ? CQ_STAGED_G36 : CQ_STAGED_G45);
 };
 
@@ -201,6 +206,9 @@ struct StagedShape {
 #endif
 #ifndef CQ_MOMENT_NPW3   // stage slots (= producer warps)
 #define CQ_MOMENT_NPW3 4
+#endif
+#ifndef CQ_MOMENT_NPW3_SHORT  // ... for rules of at most 12 points per cell on average
+#define CQ_MOMENT_NPW3_SHORT 6
 #endif
 #ifndef CQ_MOMENT_NMW3
 #define CQ_MOMENT_NMW3 4
@@ -260,8 +268,14 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
     }
     // ... and on Q1 hexahedra (create_box meshes): 27 moments, two expansion roles
     if constexpr (T::DIM == 3 && T::DEG == 1 && (T::FORM_ID == CQ_FORM_MASS || T::FORM_ID == CQ_FORM_STIFFNESS)) {
-      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3)
+      if ((P.mesh_flags & MESH_AXIS_ALIGNED) && ctx->variant != 3) {
+        // short rules (the 8-point bulk rule of config 5): the stages are small and the ring is bound by the stage
+        // rate, not by bytes -> six slots (measured on 128^3 cells, 8 points: stiffness 0.513 -> 0.475 ms, mass
+        // 0.491 -> 0.466 ms; with U{8..27} points six slots no longer hold a stage and cost 0.60 -> 0.80 ms)
+        if (P.num_points <= 12 * P.num_entries)
+          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
         return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
+      }
     }
     return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);
   }
