@@ -177,8 +177,17 @@ def cpu_baseline_sample():
     for _, form, deg in fl:
         oracle.assemble_matrix(form, [qr], nthreads=threads, pattern=pats[deg])
     dt = time.perf_counter() - t0
+    # one core (the reference's cell loop is serial, assemble_matrix.py:84): the first 64 columns of the same slab
+    n1 = 64 * MESH_N
+    q1 = qr.select(np.arange(n1))
+    t1 = time.perf_counter()
+    for _, form, deg in fl:
+        oracle.assemble_matrix(form, [q1], nthreads=1, pattern=pats[deg])
+    dt1 = time.perf_counter() - t1
     return {"value": len(fl) * mesh.num_cells / dt, "unit": "element tensors/s", "cores": threads, "kind": "port", "seconds": dt,
-            "sample": f"{cols}x{MESH_N} cell slab ({mesh.num_cells} cells, {qr.num_points} points) of the workload, all 4 forms once; oracle/cq_oracle.c allocation-free flavour, OpenMP over cells"}  # fmt: skip
+            "sample": f"{cols}x{MESH_N} cell slab ({mesh.num_cells} cells, {qr.num_points} points) of the workload, all 4 forms once; oracle/cq_oracle.c allocation-free flavour, OpenMP over cells",
+            "single_core": {"value": len(fl) * n1 / dt1, "unit": "element tensors/s", "cores": 1, "seconds": dt1,
+                            "sample": f"64x{MESH_N} cell slab ({n1} cells, {q1.num_points} points), all 4 forms once"}}  # fmt: skip
 
 
 # ------------------------------------------------------------------------------------------------
