@@ -39,6 +39,11 @@ class CsrDesc(C.Structure):
         super().__init__(num_rows, nnz, indptr, indices, values, num_rows if peer_row0 is None else peer_row0, peer_rowstart)
 
 
+class CircleDesc(C.Structure):
+    _fields_ = [("xmin", C.c_double * 2), ("h", C.c_double * 2), ("n", C.c_int64 * 2), ("center", C.c_double * 2), ("radius", C.c_double),
+                ("n1", C.c_int32), ("pad_", C.c_int32), ("g", C.c_double * 8), ("gw", C.c_double * 8)]  # fmt: skip
+
+
 class CqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libcq_b200 error {code}: {msg}")
@@ -73,6 +78,8 @@ _SIGNATURES = {
     "cq_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "cq_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cq_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cq_circle_classify": (C.c_int, [C.c_void_p, C.POINTER(CircleDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_circle_rules": (C.c_int, [C.c_void_p, C.POINTER(CircleDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_matrix_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_vector_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),

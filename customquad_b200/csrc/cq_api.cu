@@ -7,6 +7,7 @@
 #include <new>
 
 #include "cq_internal.h"
+#include "cq_levelset.cuh"
 
 namespace cq {
 
@@ -130,6 +131,29 @@ __global__ void classify_kernel(const KParams P, int64_t num_cells, int* flag) {
       for (int k = 0; k < DIM; ++k) ok = ok && (k == e ? geo.c[1 << e][k] != 0.0 : geo.c[1 << e][k] == 0.0);
   }
   if (!ok) atomicAnd(flag, 0);
+}
+
+// cut-cell quadrature of a disk (cq_levelset.cuh): one thread per cell / per cut cell
+__global__ void circle_classify_kernel(const CircleGrid G, const int64_t ncells, int32_t* __restrict__ cls, int32_t* __restrict__ nbulk,
+                                       int32_t* __restrict__ nsurf) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  int32_t nb, ns;
+  cls[c] = ls_classify_count(G, c, &nb, &ns);
+  nbulk[c] = nb;
+  nsurf[c] = ns;
+}
+
+__global__ void circle_rules_kernel(const CircleGrid G, const int64_t ncut, const int32_t* __restrict__ cut_cells,
+                                    const int64_t* __restrict__ off_bulk, const int64_t* __restrict__ off_surf, double* __restrict__ pts,
+                                    double* __restrict__ w, double* __restrict__ pts_b, double* __restrict__ w_b, double* __restrict__ nrm) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncut) return;
+  double lo[2], hi[2], wsum;
+  ls_cell_box(G, cut_cells[k], lo, hi);
+  const int64_t ob = off_bulk[k], os = off_surf[k];
+  ls_bulk_rule(G, lo, hi, pts + 2 * ob, w + ob, &wsum);
+  ls_surface_rule(G, lo, hi, pts_b + 2 * os, w_b + os, nrm + 2 * os);
 }
 
 // scatter positions: one thread per (cell, i, j)
@@ -479,6 +503,37 @@ int cq_ipc_close(cq_ctx* ctx, void* mapped_base) {
   if (!ctx || !mapped_base) return CQ_OK;
   if (int rc = set_device(ctx)) return rc;
   return check_cuda(cudaIpcCloseMemHandle(mapped_base), "cudaIpcCloseMemHandle");
+}
+
+static_assert(sizeof(cq_circle) == sizeof(CircleGrid), "cq_circle (C-ABI) and cq::CircleGrid must have the same layout");
+
+int cq_circle_classify(cq_ctx* ctx, const cq_circle* grid, int32_t* cls, int32_t* nbulk, int32_t* nsurf, void* stream) {
+  if (!ctx || !grid || !cls || !nbulk || !nsurf) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (grid->n1 < 2 || grid->n1 > LS_MAX_N1 || grid->n[0] < 0 || grid->n[1] < 0 || !(grid->h[0] > 0.0) || !(grid->h[1] > 0.0) || !(grid->radius > 0.0)) {
+    set_error("bad cq_circle (n1 in 2..8, positive cell size and radius)");
+    return CQ_ERR_INVALID;
+  }
+  const int64_t ncells = grid->n[0] * grid->n[1];
+  if (ncells == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  const int64_t blocks = (ncells + 255) / 256;
+  circle_classify_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*reinterpret_cast<const CircleGrid*>(grid), ncells, cls, nbulk, nsurf);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "circle_classify_kernel launch");
+}
+
+int cq_circle_rules(cq_ctx* ctx, const cq_circle* grid, int64_t ncut, const int32_t* cut_cells, const int64_t* off_bulk,
+                    const int64_t* off_surf, double* pts, double* w, double* pts_b, double* w_b, double* nrm, void* stream) {
+  if (!ctx || !grid || ncut < 0) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (ncut == 0) return CQ_OK;
+  if (!cut_cells || !off_bulk || !off_surf || !pts || !w || !pts_b || !w_b || !nrm) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (grid->n1 < 2 || grid->n1 > LS_MAX_N1) { set_error("bad cq_circle.n1"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  const int64_t blocks = (ncut + 127) / 128;
+  circle_rules_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(*reinterpret_cast<const CircleGrid*>(grid), ncut, cut_cells, off_bulk, off_surf, pts, w,
+                                                                                     pts_b, w_b, nrm);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "circle_rules_kernel launch");
 }
 
 int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream) {

@@ -267,3 +267,69 @@ def generate_qr_circle(mesh, radius=1.0, center=(0.0, 0.0), order=4):
     cut_cells = np.asarray(keep, dtype=np.int32)
     return (cut_cells, np.nonzero(uncut)[0].astype(np.int32), np.nonzero(outside)[0].astype(np.int32),
             qr_pts, qr_w, qr_pts_b, qr_w_b, qr_n)  # fmt: skip
+
+
+def circle_desc(mesh, radius=1.0, center=(0.0, 0.0), order=4):
+    """The ``cq_circle`` argument of cq_circle_classify / cq_circle_rules (include/cq_b200.h) for a tensor mesh."""
+    from . import _lib
+
+    assert mesh.topology.dim == 2, "circle: 2-D meshes"
+    n1 = max(2, (order + 2) // 2)
+    assert n1 <= 8, "at most 8 Gauss points per direction"
+    g, gw = _gauss01(n1)
+    h = mesh.h()
+    D = _lib.CircleDesc()
+    D.xmin[:] = [float(mesh.xmin[0]), float(mesh.xmin[1])]
+    D.h[:] = [float(h[0]), float(h[1])]
+    D.n[:] = [int(mesh.shape[0]), int(mesh.shape[1])]
+    D.center[:] = [float(center[0]), float(center[1])]
+    D.radius = float(radius)
+    D.n1 = n1
+    D.g[:n1] = list(g)
+    D.gw[:n1] = list(gw)
+    return D
+
+
+def generate_qr_circle_device(mesh, radius=1.0, center=(0.0, 0.0), order=4):
+    """``generate_qr_circle`` on the GPU (cq_circle_classify + cq_circle_rules, csrc/cq_levelset.cuh): the same
+    classification and rules, produced in HBM in the ragged layout the assembly kernels read.
+
+    Returns (cut_cells, uncut_cells, outside_cells, qr_bulk, qr_bdry): int32 numpy cell lists and two
+    ``RaggedQuadrature`` objects (bulk: points + weights; bdry: points + weights + unit normals) whose device copies
+    are already in place -- ``assemble_*(form, [qr_bulk])`` uploads nothing."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    from .quadrature import RaggedQuadrature
+
+    L = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ctx = _lib.ctx(dev.index)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    D = circle_desc(mesh, radius, center, order)
+    ncells = mesh.num_cells
+    cls = torch.empty(ncells, dtype=torch.int32, device=dev)
+    nb = torch.empty(ncells, dtype=torch.int32, device=dev)
+    ns = torch.empty(ncells, dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(L.cq_circle_classify(ctx, C.byref(D), p(cls), p(nb), p(ns), stream))
+    cut = torch.nonzero(cls == 1).reshape(-1).to(torch.int32)
+    ncut = int(cut.shape[0])
+    off_b = torch.zeros(ncut + 1, dtype=torch.int64, device=dev)
+    off_s = torch.zeros(ncut + 1, dtype=torch.int64, device=dev)
+    if ncut:
+        off_b[1:] = torch.cumsum(nb[cut.long()].to(torch.int64), 0)
+        off_s[1:] = torch.cumsum(ns[cut.long()].to(torch.int64), 0)
+    Pb, Ps = int(off_b[-1]), int(off_s[-1])
+    f64 = lambda n: torch.empty(max(n, 1), dtype=torch.float64, device=dev)[:n]  # noqa: E731
+    pts, w, pts_b, w_b, nrm = f64(2 * Pb), f64(Pb), f64(2 * Ps), f64(Ps), f64(2 * Ps)
+    _lib.check(L.cq_circle_rules(ctx, C.byref(D), ncut, p(cut), p(off_b), p(off_s), p(pts), p(w), p(pts_b), p(w_b), p(nrm), stream))
+    host = lambda t: t.cpu().numpy()  # noqa: E731
+    qb = RaggedQuadrature(host(cut), host(off_b), host(pts), host(w), None, 2)
+    qs = RaggedQuadrature(host(cut), host(off_s), host(pts_b), host(w_b), host(nrm), 2)
+    qb._dev[dev] = (cut, off_b, pts, w, None)
+    qs._dev[dev] = (cut, off_s, pts_b, w_b, nrm)
+    c = host(cls)
+    return (host(cut), np.nonzero(c == 2)[0].astype(np.int32), np.nonzero(c == 0)[0].astype(np.int32), qb, qs)

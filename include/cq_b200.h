@@ -251,6 +251,36 @@ int cq_ipc_export(cq_ctx* ctx, const void* dev_ptr, unsigned char handle[64], in
 int cq_ipc_open(cq_ctx* ctx, const unsigned char handle[64], int64_t offset, void** mapped_ptr, void** mapped_base);
 int cq_ipc_close(cq_ctx* ctx, void* mapped_base);
 
+/* ---- cut-cell quadrature producer (the step in front of the path) --------
+ * What the reference's demo gets from Algoim: demo/algoim_utils.hpp:84-153 with the level set of
+ * demo/circle.hpp:14-34, phi = |x - center|^2 - radius^2, on a tensor quadrilateral mesh with cell
+ * id = ix * n[1] + iy (dolfinx create_rectangle order).  Own scheme (Algoim is not available):
+ * customquad_b200/csrc/cq_levelset.cuh.  g / gw: Gauss-Legendre nodes / weights on [0, 1].        */
+typedef struct cq_circle {
+  double xmin[2];
+  double h[2];
+  int64_t n[2];
+  double center[2];
+  double radius;
+  int32_t n1;              /* Gauss points per direction, 2..8 */
+  int32_t pad_;
+  double g[8];
+  double gw[8];
+} cq_circle;
+/* Pass 1, one thread per cell: cls[c] = 0 outside / 1 cut / 2 uncut (algoim_utils.hpp:98-100,
+ * 145-152); nbulk[c] / nsurf[c] = points of the bulk / surface rule of a cut cell (0 otherwise).
+ * All three [n[0]*n[1]] int32 on the device. */
+int cq_circle_classify(cq_ctx* ctx, const cq_circle* grid, int32_t* cls, int32_t* nbulk,
+                       int32_t* nsurf, void* stream);
+/* Pass 2, one thread per cut cell k (cell cut_cells[k]): the bulk rule into pts[2*off_bulk[k]..],
+ * w[off_bulk[k]..] and the surface rule into pts_b / w_b / nrm at off_surf[k]: points in unit-cell
+ * coordinates (algoim_utils.hpp:134-143), weights relative to the cell volume (:127-132), unit
+ * outward normals -- the qr_pts / qr_w / qr_n arrays of a qr_data tuple in ragged form, device
+ * resident, ready for cq_assemble_*. */
+int cq_circle_rules(cq_ctx* ctx, const cq_circle* grid, int64_t ncut, const int32_t* cut_cells,
+                    const int64_t* off_bulk, const int64_t* off_surf, double* pts, double* w,
+                    double* pts_b, double* w_b, double* nrm, void* stream);
+
 /* ---- end-to-end entry points (HOST pointers; copies are part of the call) ------------------
  * The reference-facing call with host buffers: qr arrays, and the result, live in (ideally
  * pinned) host memory; mesh/space/pattern are device-resident setup data like the PETSc Mat

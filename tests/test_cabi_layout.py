@@ -13,6 +13,7 @@ STRUCTS = {
     "cq_space": ("SpaceDesc", ["num_dofs", "dofmap", "coeffs", "elem_pos"]),
     "cq_quadrature": ("QuadratureDesc", ["num_entries", "num_points", "cells", "offsets", "pts", "weights", "normals"]),
     "cq_csr": ("CsrDesc", ["num_rows", "nnz", "indptr", "indices", "values", "peer_row0", "peer_rowstart"]),
+    "cq_circle": ("CircleDesc", ["xmin", "h", "n", "center", "radius", "n1", "pad_", "g", "gw"]),
 }
 
 
