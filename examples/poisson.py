@@ -22,17 +22,24 @@ import numpy as np
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import customquad_b200 as cq  # noqa: E402
 from customquad_b200 import cutfem, forms, utils  # noqa: E402
-from customquad_b200.levelset import generate_qr_circle, generate_qr_sphere  # noqa: E402
+from customquad_b200.levelset import generate_qr_circle, generate_qr_circle_device, generate_qr_sphere  # noqa: E402
 
 
-def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle"):
+def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
+    """qr = "device" (circle): the rules come from the GPU producer (cq_circle_classify / cq_circle_rules) and stay in HBM."""
     import scipy.sparse.linalg as spla
 
+    device_rules = None
     if domain == "circle":  # demo/poisson.py:39-50
         xmin, xmax = np.array([-1.11, -1.51]), np.array([1.55, 1.22])
         volume_exact, area_exact = np.pi, 2 * np.pi
         mesh = cq.create_rectangle([xmin, xmax], [N, N])
-        rules = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
+        if qr == "device":
+            cut, uncut, outside, qb, qs = generate_qr_circle_device(mesh, 1.0, (0.0, 0.0), order)
+            device_rules = (qb, qs)
+            rules = (cut, uncut, outside, None, np.split(qb.w, qb.offsets[1:-1]), None, np.split(qs.w, qs.offsets[1:-1]), None)
+        else:
+            rules = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
     else:
         xmin, xmax = np.array([-1.11, -1.51, -1.23]), np.array([1.55, 1.22, 1.11])
         volume_exact, area_exact = 4 * np.pi / 3, 4 * np.pi
@@ -46,8 +53,8 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle"):
     g = cq.Function(V).interpolate(lambda x: np.prod(np.sin(np.pi * x[:gdim]), axis=0))  # (:146)
 
     qr_uncut = cutfem.standard_rule(mesh, uncut_cells, 2)  # dx_uncut: dolfinx's default degree for Q1 x Q1 gradients
-    qr_bulk = [(cut_cells, qr_pts, qr_w)]
-    qr_bdry = [(cut_cells, qr_pts_bdry, qr_w_bdry, qr_n)]
+    qr_bulk = [(cut_cells, qr_pts, qr_w)] if device_rules is None else [device_rules[0]]
+    qr_bdry = [(cut_cells, qr_pts_bdry, qr_w_bdry, qr_n)] if device_rules is None else [device_rules[1]]
 
     # matrices: uncut bulk + cut bulk + Nitsche boundary (A = Ax + Ac1 + Ac2, :203-205)
     A = cq.assemble_matrix(forms.stiffness(V), [qr_uncut])
@@ -96,5 +103,6 @@ if __name__ == "__main__":
     ap.add_argument("-betaN", type=float, default=10.0)
     ap.add_argument("-betas", type=float, default=1.0)
     ap.add_argument("-domain", default="circle", choices=["circle", "sphere"])  # demo/poisson.py:17
+    ap.add_argument("-qr", default="host", choices=["host", "device"], help="circle: where the cut-cell rules are produced")
     a = ap.parse_args()
-    print(json.dumps(solve(a.N, a.betaN, a.betas, domain=a.domain)))
+    print(json.dumps(solve(a.N, a.betaN, a.betas, domain=a.domain, qr=a.qr)))

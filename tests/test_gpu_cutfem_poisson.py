@@ -30,6 +30,18 @@ def test_poisson_circle_converges(cuda_backend):
     assert l2[-1] < 5e-3 and h1[-1] < 0.25  # measured: 3.07e-3, 0.175 at N = 64
 
 
+def test_poisson_circle_with_device_rules(cuda_backend):
+    """The same solve with the rules produced on the GPU and left in HBM (examples/poisson.py -qr device)."""
+    import poisson
+
+    a, b = poisson.solve(32), poisson.solve(32, qr="device")
+    assert a["cut_cells"] == b["cut_cells"] and a["uncut_cells"] == b["uncut_cells"]
+    for k in ("L2_err", "H10_err"):
+        assert abs(a[k] - b[k]) <= 1e-8 * a[k], (k, a[k], b[k])
+    for k in ("functional_volume_err", "functional_area_err", "qr_volume_err", "qr_area_err"):
+        assert abs(a[k] - b[k]) < 1e-11, (k, a[k], b[k])
+
+
 def test_poisson_sphere_converges(cuda_backend):
     """-domain sphere (demo/poisson.py:45-49): Q1 hexahedra -- the 27-moment mass / stiffness kernel, the 4-set
     Nitsche moment kernel with quadrature normals, hex load vectors and functionals -- in the demo's own setting."""
