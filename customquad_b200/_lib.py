@@ -44,6 +44,11 @@ class CircleDesc(C.Structure):
                 ("n1", C.c_int32), ("pad_", C.c_int32), ("g", C.c_double * 8), ("gw", C.c_double * 8)]  # fmt: skip
 
 
+class SphereDesc(C.Structure):
+    _fields_ = [("xmin", C.c_double * 3), ("h", C.c_double * 3), ("n", C.c_int64 * 3), ("center", C.c_double * 3), ("radius", C.c_double),
+                ("n1", C.c_int32), ("axis", C.c_int32), ("g", C.c_double * 8), ("gw", C.c_double * 8), ("gu", C.c_double * 10), ("gwu", C.c_double * 10)]  # fmt: skip
+
+
 class CqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libcq_b200 error {code}: {msg}")
@@ -80,6 +85,8 @@ _SIGNATURES = {
     "cq_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cq_circle_classify": (C.c_int, [C.c_void_p, C.POINTER(CircleDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_circle_rules": (C.c_int, [C.c_void_p, C.POINTER(CircleDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_sphere_classify": (C.c_int, [C.c_void_p, C.POINTER(SphereDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_sphere_rules": (C.c_int, [C.c_void_p, C.POINTER(SphereDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_matrix_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_vector_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),

@@ -156,6 +156,28 @@ __global__ void circle_rules_kernel(const CircleGrid G, const int64_t ncut, cons
   ls_surface_rule(G, lo, hi, pts_b + 2 * os, w_b + os, nrm + 2 * os);
 }
 
+__global__ void sphere_classify_kernel(const SphereGrid G, const int64_t ncells, int32_t* __restrict__ cls, int32_t* __restrict__ nbulk,
+                                       int32_t* __restrict__ nsurf) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  int32_t nb, ns;
+  cls[c] = ls_classify_count3(G, c, &nb, &ns);
+  nbulk[c] = nb;
+  nsurf[c] = ns;
+}
+
+__global__ void sphere_rules_kernel(const SphereGrid G, const int64_t ncut, const int32_t* __restrict__ cut_cells,
+                                    const int64_t* __restrict__ off_bulk, const int64_t* __restrict__ off_surf, double* __restrict__ pts,
+                                    double* __restrict__ w, double* __restrict__ pts_b, double* __restrict__ w_b, double* __restrict__ nrm) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncut) return;
+  double lo[3], hi[3], wsum;
+  int nb, ns;
+  ls_cell_box3(G, cut_cells[k], lo, hi);
+  const int64_t ob = off_bulk[k], os = off_surf[k];
+  ls_sphere_rules(G, lo, hi, pts + 3 * ob, w + ob, pts_b + 3 * os, w_b + os, nrm + 3 * os, &nb, &ns, &wsum);
+}
+
 // scatter positions: one thread per (cell, i, j)
 __global__ void scatter_map_kernel(const int32_t* __restrict__ dofmap, int64_t num_cells, int n, int stride, int bs,
                                    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -534,6 +556,38 @@ int cq_circle_rules(cq_ctx* ctx, const cq_circle* grid, int64_t ncut, const int3
                                                                                      pts_b, w_b, nrm);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "circle_rules_kernel launch");
+}
+
+static_assert(sizeof(cq_sphere) == sizeof(SphereGrid), "cq_sphere (C-ABI) and cq::SphereGrid must have the same layout");
+
+int cq_sphere_classify(cq_ctx* ctx, const cq_sphere* grid, int32_t* cls, int32_t* nbulk, int32_t* nsurf, void* stream) {
+  if (!ctx || !grid || !cls || !nbulk || !nsurf) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (grid->n1 < 2 || grid->n1 > LS_MAX_N1 || grid->axis < 0 || grid->axis > 2 || !(grid->radius > 0.0) || !(grid->h[0] > 0.0) || !(grid->h[1] > 0.0) ||
+      !(grid->h[2] > 0.0) || grid->n[0] < 0 || grid->n[1] < 0 || grid->n[2] < 0) {
+    set_error("bad cq_sphere (n1 in 2..8, axis in 0..2, positive cell size and radius)");
+    return CQ_ERR_INVALID;
+  }
+  const int64_t ncells = grid->n[0] * grid->n[1] * grid->n[2];
+  if (ncells == 0) return CQ_OK;
+  if (int rc = set_device(ctx)) return rc;
+  const int64_t blocks = (ncells + 127) / 128;
+  sphere_classify_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(*reinterpret_cast<const SphereGrid*>(grid), ncells, cls, nbulk, nsurf);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "sphere_classify_kernel launch");
+}
+
+int cq_sphere_rules(cq_ctx* ctx, const cq_sphere* grid, int64_t ncut, const int32_t* cut_cells, const int64_t* off_bulk,
+                    const int64_t* off_surf, double* pts, double* w, double* pts_b, double* w_b, double* nrm, void* stream) {
+  if (!ctx || !grid || ncut < 0) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (ncut == 0) return CQ_OK;
+  if (!cut_cells || !off_bulk || !off_surf || !pts || !w || !pts_b || !w_b || !nrm) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (grid->n1 < 2 || grid->n1 > LS_MAX_N1 || grid->axis < 0 || grid->axis > 2) { set_error("bad cq_sphere"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  const int64_t blocks = (ncut + 63) / 64;
+  sphere_rules_kernel<<<(unsigned)blocks, 64, 0, static_cast<cudaStream_t>(stream)>>>(*reinterpret_cast<const SphereGrid*>(grid), ncut, cut_cells, off_bulk, off_surf, pts, w, pts_b,
+                                                                                    w_b, nrm);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "sphere_rules_kernel launch");
 }
 
 int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream) {

@@ -290,13 +290,34 @@ def circle_desc(mesh, radius=1.0, center=(0.0, 0.0), order=4):
     return D
 
 
-def generate_qr_circle_device(mesh, radius=1.0, center=(0.0, 0.0), order=4):
-    """``generate_qr_circle`` on the GPU (cq_circle_classify + cq_circle_rules, csrc/cq_levelset.cuh): the same
-    classification and rules, produced in HBM in the ragged layout the assembly kernels read.
+def sphere_desc(mesh, radius=1.0, center=(0.0, 0.0, 0.0), order=4, axis=2):
+    """The ``cq_sphere`` argument of cq_sphere_classify / cq_sphere_rules for a tensor hexahedral mesh."""
+    from . import _lib
 
-    Returns (cut_cells, uncut_cells, outside_cells, qr_bulk, qr_bdry): int32 numpy cell lists and two
-    ``RaggedQuadrature`` objects (bulk: points + weights; bdry: points + weights + unit normals) whose device copies
-    are already in place -- ``assemble_*(form, [qr_bulk])`` uploads nothing."""
+    assert mesh.topology.dim == 3, "sphere: 3-D meshes"
+    n1 = max(2, (order + 2) // 2)
+    assert n1 <= 8, "at most 8 Gauss points per direction"
+    g, gw = _gauss01(n1)
+    gu, gwu = _gauss01(n1 + 2)
+    h = mesh.h()
+    D = _lib.SphereDesc()
+    D.xmin[:] = [float(v) for v in mesh.xmin[:3]]
+    D.h[:] = [float(v) for v in h[:3]]
+    D.n[:] = [int(v) for v in mesh.shape[:3]]
+    D.center[:] = [float(v) for v in center]
+    D.radius = float(radius)
+    D.n1 = n1
+    D.axis = int(axis)
+    D.g[:n1] = list(g)
+    D.gw[:n1] = list(gw)
+    D.gu[: n1 + 2] = list(gu)
+    D.gwu[: n1 + 2] = list(gwu)
+    return D
+
+
+def _produce_on_device(mesh, D, classify, rules, gdim):
+    """Two passes: per-cell classification + point counts, prefix sums, then the rules of the cut cells written
+    into the ragged layout of a qr tuple.  Everything stays in HBM; the cell lists also come back to the host."""
     import ctypes as C
 
     import torch
@@ -304,17 +325,15 @@ def generate_qr_circle_device(mesh, radius=1.0, center=(0.0, 0.0), order=4):
     from . import _lib
     from .quadrature import RaggedQuadrature
 
-    L = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device())
     ctx = _lib.ctx(dev.index)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    D = circle_desc(mesh, radius, center, order)
     ncells = mesh.num_cells
     cls = torch.empty(ncells, dtype=torch.int32, device=dev)
     nb = torch.empty(ncells, dtype=torch.int32, device=dev)
     ns = torch.empty(ncells, dtype=torch.int32, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-    _lib.check(L.cq_circle_classify(ctx, C.byref(D), p(cls), p(nb), p(ns), stream))
+    _lib.check(classify(ctx, C.byref(D), p(cls), p(nb), p(ns), stream))
     cut = torch.nonzero(cls == 1).reshape(-1).to(torch.int32)
     ncut = int(cut.shape[0])
     off_b = torch.zeros(ncut + 1, dtype=torch.int64, device=dev)
@@ -324,12 +343,34 @@ def generate_qr_circle_device(mesh, radius=1.0, center=(0.0, 0.0), order=4):
         off_s[1:] = torch.cumsum(ns[cut.long()].to(torch.int64), 0)
     Pb, Ps = int(off_b[-1]), int(off_s[-1])
     f64 = lambda n: torch.empty(max(n, 1), dtype=torch.float64, device=dev)[:n]  # noqa: E731
-    pts, w, pts_b, w_b, nrm = f64(2 * Pb), f64(Pb), f64(2 * Ps), f64(Ps), f64(2 * Ps)
-    _lib.check(L.cq_circle_rules(ctx, C.byref(D), ncut, p(cut), p(off_b), p(off_s), p(pts), p(w), p(pts_b), p(w_b), p(nrm), stream))
+    pts, w, pts_b, w_b, nrm = f64(gdim * Pb), f64(Pb), f64(gdim * Ps), f64(Ps), f64(gdim * Ps)
+    _lib.check(rules(ctx, C.byref(D), ncut, p(cut), p(off_b), p(off_s), p(pts), p(w), p(pts_b), p(w_b), p(nrm), stream))
     host = lambda t: t.cpu().numpy()  # noqa: E731
-    qb = RaggedQuadrature(host(cut), host(off_b), host(pts), host(w), None, 2)
-    qs = RaggedQuadrature(host(cut), host(off_s), host(pts_b), host(w_b), host(nrm), 2)
+    qb = RaggedQuadrature(host(cut), host(off_b), host(pts), host(w), None, gdim)
+    qs = RaggedQuadrature(host(cut), host(off_s), host(pts_b), host(w_b), host(nrm), gdim)
     qb._dev[dev] = (cut, off_b, pts, w, None)
     qs._dev[dev] = (cut, off_s, pts_b, w_b, nrm)
     c = host(cls)
     return (host(cut), np.nonzero(c == 2)[0].astype(np.int32), np.nonzero(c == 0)[0].astype(np.int32), qb, qs)
+
+
+def generate_qr_sphere_device(mesh, radius=1.0, center=(0.0, 0.0, 0.0), order=4, axis=2):
+    """``generate_qr_sphere`` on the GPU (cq_sphere_classify + cq_sphere_rules); same return value as
+    ``generate_qr_circle_device``."""
+    from . import _lib
+
+    L = _lib.load()
+    return _produce_on_device(mesh, sphere_desc(mesh, radius, center, order, axis), L.cq_sphere_classify, L.cq_sphere_rules, 3)
+
+
+def generate_qr_circle_device(mesh, radius=1.0, center=(0.0, 0.0), order=4):
+    """``generate_qr_circle`` on the GPU (cq_circle_classify + cq_circle_rules, csrc/cq_levelset.cuh): the same
+    classification and rules, produced in HBM in the ragged layout the assembly kernels read.
+
+    Returns (cut_cells, uncut_cells, outside_cells, qr_bulk, qr_bdry): int32 numpy cell lists and two
+    ``RaggedQuadrature`` objects (bulk: points + weights; bdry: points + weights + unit normals) whose device copies
+    are already in place -- ``assemble_*(form, [qr_bulk])`` uploads nothing."""
+    from . import _lib
+
+    L = _lib.load()
+    return _produce_on_device(mesh, circle_desc(mesh, radius, center, order), L.cq_circle_classify, L.cq_circle_rules, 2)

@@ -22,11 +22,16 @@ import numpy as np
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import customquad_b200 as cq  # noqa: E402
 from customquad_b200 import cutfem, forms, utils  # noqa: E402
-from customquad_b200.levelset import generate_qr_circle, generate_qr_circle_device, generate_qr_sphere  # noqa: E402
+from customquad_b200.levelset import (  # noqa: E402
+    generate_qr_circle,
+    generate_qr_circle_device,
+    generate_qr_sphere,
+    generate_qr_sphere_device,
+)
 
 
 def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
-    """qr = "device" (circle): the rules come from the GPU producer (cq_circle_classify / cq_circle_rules) and stay in HBM."""
+    """qr = "device": the rules come from the GPU producer (cq_circle_* / cq_sphere_*) and stay in HBM."""
     import scipy.sparse.linalg as spla
 
     device_rules = None
@@ -44,7 +49,12 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
         xmin, xmax = np.array([-1.11, -1.51, -1.23]), np.array([1.55, 1.22, 1.11])
         volume_exact, area_exact = 4 * np.pi / 3, 4 * np.pi
         mesh = cq.create_box([xmin, xmax], [N, N, N])
-        rules = generate_qr_sphere(mesh, 1.0, (0.0, 0.0, 0.0), order)
+        if qr == "device":
+            cut, uncut, outside, qb, qs = generate_qr_sphere_device(mesh, 1.0, (0.0, 0.0, 0.0), order)
+            device_rules = (qb, qs)
+            rules = (cut, uncut, outside, None, np.split(qb.w, qb.offsets[1:-1]), None, np.split(qs.w, qs.offsets[1:-1]), None)
+        else:
+            rules = generate_qr_sphere(mesh, 1.0, (0.0, 0.0, 0.0), order)
     gdim = len(xmin)
     cut_cells, uncut_cells, outside_cells, qr_pts, qr_w, qr_pts_bdry, qr_w_bdry, qr_n = rules
     V = cq.FunctionSpace(mesh, ("Lagrange", 1))
@@ -103,6 +113,6 @@ if __name__ == "__main__":
     ap.add_argument("-betaN", type=float, default=10.0)
     ap.add_argument("-betas", type=float, default=1.0)
     ap.add_argument("-domain", default="circle", choices=["circle", "sphere"])  # demo/poisson.py:17
-    ap.add_argument("-qr", default="host", choices=["host", "device"], help="circle: where the cut-cell rules are produced")
+    ap.add_argument("-qr", default="host", choices=["host", "device"], help="where the cut-cell rules are produced")
     a = ap.parse_args()
     print(json.dumps(solve(a.N, a.betaN, a.betas, domain=a.domain, qr=a.qr)))

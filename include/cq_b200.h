@@ -281,6 +281,29 @@ int cq_circle_rules(cq_ctx* ctx, const cq_circle* grid, int64_t ncut, const int3
                     const int64_t* off_bulk, const int64_t* off_surf, double* pts, double* w,
                     double* pts_b, double* w_b, double* nrm, void* stream);
 
+/* The same for a ball on a tensor hexahedral mesh (demo/sphere.hpp:14-34; cell id = (iz*n[1] + iy)*n[0] + ix,
+ * dolfinx create_box order): the ball is sliced along `axis`, the cross-sections are disk-rectangle problems.
+ * gu / gwu: Gauss-Legendre on [0, 1] with n1 + 2 points (slicing variable). */
+typedef struct cq_sphere {
+  double xmin[3];
+  double h[3];
+  int64_t n[3];
+  double center[3];
+  double radius;
+  int32_t n1;
+  int32_t axis;
+  double g[8];
+  double gw[8];
+  double gu[10];
+  double gwu[10];
+} cq_sphere;
+int cq_sphere_classify(cq_ctx* ctx, const cq_sphere* grid, int32_t* cls, int32_t* nbulk,
+                       int32_t* nsurf, void* stream);
+/* points / normals: 3 doubles per point */
+int cq_sphere_rules(cq_ctx* ctx, const cq_sphere* grid, int64_t ncut, const int32_t* cut_cells,
+                    const int64_t* off_bulk, const int64_t* off_surf, double* pts, double* w,
+                    double* pts_b, double* w_b, double* nrm, void* stream);
+
 /* ---- end-to-end entry points (HOST pointers; copies are part of the call) ------------------
  * The reference-facing call with host buffers: qr arrays, and the result, live in (ideally
  * pinned) host memory; mesh/space/pattern are device-resident setup data like the PETSc Mat

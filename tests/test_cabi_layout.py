@@ -14,6 +14,7 @@ STRUCTS = {
     "cq_quadrature": ("QuadratureDesc", ["num_entries", "num_points", "cells", "offsets", "pts", "weights", "normals"]),
     "cq_csr": ("CsrDesc", ["num_rows", "nnz", "indptr", "indices", "values", "peer_row0", "peer_rowstart"]),
     "cq_circle": ("CircleDesc", ["xmin", "h", "n", "center", "radius", "n1", "pad_", "g", "gw"]),
+    "cq_sphere": ("SphereDesc", ["xmin", "h", "n", "center", "radius", "n1", "axis", "g", "gw", "gu", "gwu"]),
 }
 
 

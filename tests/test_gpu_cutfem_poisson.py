@@ -42,6 +42,17 @@ def test_poisson_circle_with_device_rules(cuda_backend):
         assert abs(a[k] - b[k]) < 1e-11, (k, a[k], b[k])
 
 
+def test_poisson_sphere_with_device_rules(cuda_backend):
+    import poisson
+
+    a, b = poisson.solve(12, domain="sphere"), poisson.solve(12, domain="sphere", qr="device")
+    assert a["cut_cells"] == b["cut_cells"] and a["uncut_cells"] == b["uncut_cells"]
+    for k in ("L2_err", "H10_err"):
+        assert abs(a[k] - b[k]) <= 1e-8 * a[k], (k, a[k], b[k])
+    for k in ("functional_volume_err", "functional_area_err"):
+        assert abs(a[k] - b[k]) < 1e-10, (k, a[k], b[k])
+
+
 def test_poisson_sphere_converges(cuda_backend):
     """-domain sphere (demo/poisson.py:45-49): Q1 hexahedra -- the 27-moment mass / stiffness kernel, the 4-set
     Nitsche moment kernel with quadrature normals, hex load vectors and functionals -- in the demo's own setting."""
