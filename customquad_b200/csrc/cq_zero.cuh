@@ -11,13 +11,16 @@
 //   setup (two small kernels per call):  zero_hi[k] = max over the waves <= k of (end of the last CSR row a wave
 //     touches), i.e. values[0 .. zero_hi[k]) covers everything the waves 0..k scatter into (any cell order: a
 //     shuffled list just makes zero_hi[0] large);
-//   in the kernel:  before the expansion warps of a CTA work on wave k they zero their share of
-//     [zero_hi[k+D-1], zero_hi[k+D]) (plain coalesced stores, D = zero_ahead waves ahead), fence, and count
-//     themselves into zero_done[k+D]; before they scatter wave k they check that zero_done[k] is complete
-//     (grid * warps signals; satisfied D waves ago unless a CTA lags).  Waves 0..D-1 and the never-touched rest
-//     [zero_hi[last], nnz) are zeroed in the prologue.
+//   in the kernel (assemble_moment_split_kernel, ZW = 1):  one more warp per CTA zeroes the CTA's share of the
+//     ranges of four waves at a time (plain coalesced 16-B stores), zero_ahead waves ahead of the CTA's moment
+//     phase (paced through a shared-memory progress word), fences, and counts the CTA into zero_done[k] of those
+//     waves; before the expansion warps scatter wave k they look at the counters of the waves up to k (loaded one
+//     iteration ahead; complete long ago unless a CTA lags more than the look-ahead).  The never-touched rest
+//     [zero_hi[last], nnz) is zeroed up front.
 // The zeroed lines are still dirty in L2 when the REDs arrive a few microseconds later, so a line is written to
-// HBM once and never read.  The kernel is launched cooperatively: the wait needs all CTAs resident.
+// HBM once and never read (ncu: 9.2 -> 7.04 GB per Q2 launch).  The kernel is launched cooperatively: the wait
+// needs all CTAs resident.  Opt-in (cq_ctx_set_fused_zero): with the traffic gone the kernel is bound by its
+// stage ring and the step time does not change -- profiles/r1/fused_zero_study.md.
 #pragma once
 #include "cq_kernels.cuh"
 
