@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CQ_B200_ABI_VERSION 2
+#define CQ_B200_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------ */
 typedef enum cq_status {

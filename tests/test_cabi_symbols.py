@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/cq_b200.h but not exported"
     L.cq_abi_version.restype = ctypes.c_int
-    assert L.cq_abi_version() == 2  # 2: cq_csr.peer_row0 / peer_rowstart, cq_ipc_*
+    # 2: cq_csr.peer_row0 / peer_rowstart, cq_ipc_*; 3: cq_assemble_matrix_zero, cq_ctx_set_fused_zero, cq_circle_*, cq_sphere_*
+    assert L.cq_abi_version() == 3
     assert set(_lib._SIGNATURES) == set(declared_symbols())
 
 
