@@ -27,10 +27,12 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "cq_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "cq_b200.h")
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        base = ["gcc", "-O2", "-g", "-fPIC", "-Wall", "-std=c11", "-D_GNU_SOURCE", "-shared", "-o", so, src, "-lm"]
+        tmp = f"{so}.{os.getpid()}.tmp"  # several test processes may rebuild at once: write aside, rename atomically
+        base = ["gcc", "-O2", "-g", "-fPIC", "-Wall", "-std=c11", "-D_GNU_SOURCE", "-shared", "-o", tmp, src, "-lm"]
         r = subprocess.run(base[:1] + ["-fopenmp"] + base[1:], capture_output=True, text=True)
         if r.returncode != 0:  # toolchain without libgomp: serial oracle
             subprocess.run(base, check=True)
+        os.replace(tmp, so)
     return so
 
 
