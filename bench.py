@@ -125,7 +125,7 @@ def run_reference(args):
 
     oracle.build()
     threads = oracle.max_threads()
-    sample_cols = 192  # 192 x 2048 = 393,216 cells per step and form (~9% of the workload)
+    sample_cols = int(os.environ.get("CQ_BENCH_SAMPLE_COLS", "192"))  # 192 x 2048 = 393,216 cells per step and form (~9% of the workload); the override is for tests/test_bench_contract.py
     mesh, spaces, fl, qr, _ = build_problem(sample_cols, MESH_N)
     pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
 
