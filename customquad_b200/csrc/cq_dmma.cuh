@@ -172,13 +172,13 @@ CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, c
         if (i < N && j < N) {
           const double v = D[en][c];
           const int pij = M.pos[e][i * N + j];
-          const long long si = M.rowstart[i][e];
-          const int li = M.rowlen[i][e];
+          const long long si = M.rowstart[e][i];
+          const int li = M.rowlen[e][i];
           for (int a = 0; a < bs; ++a) red_add_f64(P.values + si + (long long)a * li + pij * bs + a, v);
           if (ti != tj) {  // diagonal tiles are full
             const int pji = M.pos[e][j * N + i];
-            const long long sj = M.rowstart[j][e];
-            const int lj = M.rowlen[j][e];
+            const long long sj = M.rowstart[e][j];
+            const int lj = M.rowlen[e][j];
             for (int a = 0; a < bs; ++a) red_add_f64(P.values + sj + (long long)a * lj + pji * bs + a, v);
           }
         }

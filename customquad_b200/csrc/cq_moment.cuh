@@ -103,8 +103,8 @@ struct ScatterRegs {
     stride = UNIT ? 1 : P.bs;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      if constexpr (UNIT) rowp[i] = P.values + M.rowstart[i][e];
-      else rowp[i] = P.values + M.rowstart[i][e] + (long long)comp * M.rowlen[i][e] + comp;
+      if constexpr (UNIT) rowp[i] = P.values + M.rowstart[e][i];
+      else rowp[i] = P.values + M.rowstart[e][i] + (long long)comp * M.rowlen[e][i] + comp;
     }
   }
   template <int I, int J>
@@ -177,9 +177,17 @@ CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const b
 // Split kernels: the moments of an entry go to the stage header, so instead of an all-reduce the
 // G lanes transpose-reduce (M (1 - 1/G) shuffles) and lane r stores its slice of the sums.
 // Q1 hexahedron: mu[(p * 3 + q) * 3 + r] = sum w t0^p t1^q t2^r, p, q, r <= 2 (39 FP64 instructions per point)
+// Position of moment k in the accumulator handed to transpose_reduce_step<MPAD, G / 2>: after the reduction lane r
+// holds in acc[kk] the sum of position r * B + kk, so moment k = kk * G + r sits at (k % G) * B + k / G.  The G lanes
+// of an entry then store G CONSECUTIVE moments per instruction (one 8 G-byte run per entry) instead of G runs a
+// multiple of 256 B apart (same banks: ncu counted 9.4 wavefronts per store of the round-1 layout, ideal 2).
+template <int G, int MPAD>
+CQ_HD constexpr int mom_slot(int k) { return (k % G) * (MPAD / G) + k / G; }
+
 template <class T, int G, int CB, int MPAD>
 CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const bool active, const int r, double (&acc)[MPAD]) {
   constexpr int Pn = 3;
+  auto S = [](int k) constexpr { return mom_slot<G, MPAD>(k); };
 #pragma unroll
   for (int k = 0; k < MPAD; ++k) acc[k] = 0.0;
   const int nq = active ? M.nq[e] : 0;
@@ -202,9 +210,9 @@ CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const 
     for (int b = 0; b < Pn; ++b)
 #pragma unroll
       for (int c = 0; c < Pn; ++c) {
-        acc[(0 * Pn + b) * Pn + c] += YZ[b][c];
-        acc[(1 * Pn + b) * Pn + c] = fma(t0, YZ[b][c], acc[(1 * Pn + b) * Pn + c]);
-        acc[(2 * Pn + b) * Pn + c] = fma(t00, YZ[b][c], acc[(2 * Pn + b) * Pn + c]);
+        acc[S((0 * Pn + b) * Pn + c)] += YZ[b][c];
+        acc[S((1 * Pn + b) * Pn + c)] = fma(t0, YZ[b][c], acc[S((1 * Pn + b) * Pn + c)]);
+        acc[S((2 * Pn + b) * Pn + c)] = fma(t00, YZ[b][c], acc[S((2 * Pn + b) * Pn + c)]);
       }
   }
 }
@@ -268,7 +276,7 @@ CQ_DEVINL void moment_accumulate_sets(StageMeta<T, CB>& M, const int e, const bo
   }
   if (mine) {
 #pragma unroll
-    for (int k = 0; k < NM1; ++k) M.mu[r * NM1 + k][e] = acc[k];
+    for (int k = 0; k < NM1; ++k) M.mu[e][r * NM1 + k] = acc[k];
   }
 }
 
@@ -288,13 +296,15 @@ CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const b
     double mu[Pn][Pn];
     moment_accumulate<T, G, CB, false>(M, e, active && compute, r, mu);
 #pragma unroll
-    for (int k = 0; k < MPAD; ++k) acc[k] = k < NM ? mu[k / Pn][k % Pn] : 0.0;
+    for (int k = 0; k < MPAD; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NM; ++k) acc[mom_slot<G, MPAD>(k)] = mu[k / Pn][k % Pn];
   }
   transpose_reduce_step<MPAD, G / 2>(acc, r);
   if (active) {
 #pragma unroll
     for (int kk = 0; kk < B; ++kk)
-      if (r * B + kk < NM) M.mu[r * B + kk][e] = acc[kk];
+      if (kk * G + r < NM) M.mu[e][kk * G + r] = acc[kk];
   }
   }
 }
@@ -413,7 +423,7 @@ CQ_DEVINL void moment_expand_rows3(const StageMeta<T, CB>& M, const int e, doubl
 #pragma unroll
     for (int q = 0; q < Pn; ++q)
 #pragma unroll
-      for (int r = 0; r < Pn; ++r) mu[p][q][r] = M.mu[(p * Pn + q) * Pn + r][e];
+      for (int r = 0; r < Pn; ++r) mu[p][q][r] = M.mu[e][(p * Pn + q) * Pn + r];
   const double kM = M.kc[0][e];
   const double kx = STIFF ? M.kc[1][e] : 0.0, ky = STIFF ? M.kc[2][e] : 0.0, kz = STIFF ? M.kc[3][e] : 0.0;
   static_for<0, 2>([&](auto C0) {
@@ -519,7 +529,7 @@ CQ_DEVINL void moment_expand_rows_nitsche(const StageMeta<T, CB>& M, const int e
           if constexpr (rc != 0.0) {
 #pragma unroll
             for (int q = 0; q < Pn; ++q) {
-              const double m = M.mu[set * NM1 + p * Pn + q][e];
+              const double m = M.mu[e][set * NM1 + p * Pn + q];
               U[set][q] = init ? fma(rc, m, U[set][q]) : rc * m;
             }
             init = true;
@@ -564,7 +574,7 @@ CQ_DEVINL void moment_expand_rows_nitsche(const StageMeta<T, CB>& M, const int e
             for (int q = 0; q < 3; ++q)
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
-                const double m = M.mu[set * NM1 + (p * 3 + q) * 3 + r][e];
+                const double m = M.mu[e][set * NM1 + (p * 3 + q) * 3 + r];
                 U[set][q][r] = init ? fma(rc, m, U[set][q][r]) : rc * m;
               }
             init = true;
@@ -642,7 +652,7 @@ CQ_DEVINL void moment_expand_rows(const StageMeta<T, CB>& M, const int e, double
 #pragma unroll
   for (int p = 0; p < Pn; ++p)
 #pragma unroll
-    for (int q = 0; q < Pn; ++q) mu[p][q] = M.mu[p * Pn + q][e];
+    for (int q = 0; q < Pn; ++q) mu[p][q] = M.mu[e][p * Pn + q];
   const double k0 = STIFF ? M.kc[1][e] : M.kc[0][e];  // stiffness: |det|/J00^2 ; mass: |det|
   const double k1 = STIFF ? M.kc[2][e] : 0.0;         // stiffness: |det|/J11^2
   static_for<0, D1>([&](auto C0) {
@@ -707,27 +717,28 @@ CQ_DEVINL void scatter_rows_transposed(const KParams& P, const StageMeta<T, CB>&
   }
   const double* tl = tile + sub * RT::STRIDE + s;
   const uint8_t* pp = &M.pos[sub][i * N + j];
-  const long long* rs = &M.rowstart[i][sub];
+  constexpr int NRP = StageMeta<T, CB>::NRP;
+  const long long* rs = &M.rowstart[sub][i];
   double* const vals = P.values;
   if (P.bs == 1) {
     if (nent == CB) {
       constexpr int UNROLL = CQ_SCATTER_UNROLL;
 #pragma unroll UNROLL
       for (int e0 = 0; e0 < CB; e0 += EPI)
-        red_add_f64(vals + rs[e0] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
+        red_add_f64(vals + rs[e0 * NRP] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
     } else {
 #pragma unroll 1
       for (int e0 = 0; e0 + sub < nent; e0 += EPI)
-        red_add_f64(vals + rs[e0] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
+        red_add_f64(vals + rs[e0 * NRP] + pp[e0 * StageMeta<T, CB>::NPOS], tl[e0 * RT::STRIDE]);
     }
   } else {
     const int bs = P.bs;
-    const int* rl = &M.rowlen[i][sub];
+    const int* rl = &M.rowlen[sub][i];
 #pragma unroll 1
     for (int e0 = 0; e0 + sub < nent; e0 += EPI) {
       const double v = tl[e0 * RT::STRIDE];
-      double* row = vals + rs[e0] + (unsigned)pp[e0 * StageMeta<T, CB>::NPOS] * bs;
-      const int len = rl[e0];
+      double* row = vals + rs[e0 * NRP] + (unsigned)pp[e0 * StageMeta<T, CB>::NPOS] * bs;
+      const int len = rl[e0 * NRP];
       for (int a = 0; a < bs; ++a) red_add_f64(row + (long long)a * len + a, v);
     }
   }

@@ -70,6 +70,14 @@ CQ_DEVINL void bulk_g2s_once(void* dst_smem, const void* src_gmem, uint32_t byte
                : "memory");
 }
 
+// L2 prefetch of a global range (bytes % 16 == 0, address 16-B aligned): the producer warps issue it for the
+// rule slice of the stage they will publish two ring turns later, so that the stage's bulk copy into shared memory
+// is an L2 hit (~0.4 us) instead of a DRAM access under load (1-2 us).  The L2 acts as the deep end of the stage
+// ring: the number of bytes in flight from HBM is no longer tied to the shared-memory slots.
+CQ_DEVINL void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ---- stage layout ------------------------------------------------------------------------------------
 template <class T, int CB>
 struct StageMeta {
@@ -85,9 +93,14 @@ struct StageMeta {
   const double* pts[CB];  // generic pointers: into this stage's shared memory, or global on overflow
   const double* w[CB];
   const double* nrm[T::NEED_NORMAL ? CB : 1];
-  double X[NV * DIM][CB];
-  long long rowstart[MAT ? N : 1][CB];  // indptr[dof_i * bs]
-  int rowlen[MAT ? N : 1][CB];          // length of that (blocked) row
+  // Entry-major with an odd row stride: the producer writes with lane = entry (stride NRP, odd: conflict-free), the
+  // transposed scatter reads with lane = value slot (a few distinct rows of ONE entry: neighbouring banks).  The
+  // round-1 layout [N][CB] put every row of an entry into the same bank (CB * 8 B = 2 x 128 B): ncu counted 4
+  // wavefronts per rowstart load of the scatter instead of 2 (12 of the 74 LSU wavefronts per Q2 cell; the kernels
+  // are bound by the LSU data pipe, profiles/r2/lsu_study.md).
+  static constexpr int NRP = (MAT ? N : 1) | 1;
+  long long rowstart[CB][NRP];  // indptr[dof_i * bs]
+  int rowlen[CB][NRP];          // length of that (blocked) row
   int dofs[VEC ? N : 1][CB];
   alignas(16) uint8_t pos[MAT ? CB : 1][MAT ? NPOS : 16];
   double coef[T::NEED_COEF ? T::NCOEF : 1][CB];
@@ -102,7 +115,13 @@ struct StageMeta {
   static constexpr int NM1 = T::DIM == 2 ? PN * PN : PN * PN * PN;  // moments per set
   static constexpr int NSET = NIT ? T::DIM + 1 : 1;
   static constexpr int NMOM = MOM ? NSET * NM1 : 1;
-  double mu[NMOM][CB];
+  static constexpr int NMP = NMOM | 1;  // entry-major, odd stride: the expansion warps read with lane = entry
+  // The vertex coordinates X are read by the point-by-point consumers only, the moments mu by the expansion warps of
+  // the moment kernels only (those work from the cell constants kc): the two share their storage.
+  union {
+    double X[NV * DIM][CB];
+    double mu[CB][NMP];
+  };
   // axis-aligned cell constants (producer): [0] |det J|; stiffness: [1 + d] |det J| / J_dd^2;
   // Nitsche: [1 + d] |det J| / J_dd (signed), [1 + DIM] |det J| betaN / h_K
   double kc[MOM ? 5 : 1][CB];
@@ -202,13 +221,13 @@ CQ_DEVINL void staged_process_entry(const KParams& P, const StageMeta<T, CB>& M,
             const int i = LE.i[kk], j = LE.j[kk];
             const double v = acc[kk];
             const unsigned pij = M.pos[e][i * N + j], pji = M.pos[e][j * N + i];
-            double* pi = P.values + M.rowstart[i][e];
-            double* pj = P.values + M.rowstart[j][e];
+            double* pi = P.values + M.rowstart[e][i];
+            double* pj = P.values + M.rowstart[e][j];
             if (bs == 1) {
               red_add_f64(pi + pij, v);
               if (i != j) red_add_f64(pj + pji, v);
             } else {
-              const int li = M.rowlen[i][e], lj = M.rowlen[j][e];
+              const int li = M.rowlen[e][i], lj = M.rowlen[e][j];
 #pragma unroll 1
               for (int a = 0; a < bs; ++a) {
                 red_add_f64(pi + (long long)a * li + pij * bs + a, v);

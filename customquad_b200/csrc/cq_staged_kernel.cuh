@@ -5,6 +5,9 @@
 #include "cq_staged.cuh"
 #include "cq_zero.cuh"
 
+#ifndef CQ_L2_PREFETCH  // 1: producers prefetch the rule slice of a stage into L2 one pipeline level before its gather (measured neutral, profiles/r2/l2_prefetch.txt: the ring is not bound by the copy latency)
+#define CQ_L2_PREFETCH 0
+#endif
 #ifndef CQ_POS_BULK_MIN  // scatter maps of at least this many bytes per cell travel by cp.async.bulk
 #define CQ_POS_BULK_MIN 64
 #endif
@@ -147,8 +150,8 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
             }
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-              M.rowstart[i][lane] = ra.rs[i];
-              M.rowlen[i][lane] = ra.rl[i];
+              M.rowstart[lane][i] = ra.rs[i];
+              M.rowlen[lane][i] = ra.rl[i];
             }
           }
           if constexpr (!KC_ONLY) {
@@ -245,6 +248,27 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         }
       }
       rb = rc;
+#if CQ_L2_PREFETCH
+      if (rb.t >= 0) {
+        // the slice this stage's bulk copies will read (same arithmetic as at publish time, rounded inwards)
+        const int64_t P0 = __shfl_sync(0xffffffffu, rb.o0, 0);
+        const int64_t P1 = __shfl_sync(0xffffffffu, rb.o1, rb.nent - 1);
+        const int64_t Pa = P0 & ~(int64_t)1;
+        int64_t cnt = (P1 - Pa) & ~(int64_t)1;
+        if (cnt > PB) cnt = PB & ~1;
+        bool pos_consec = false;
+        if constexpr (POS_BULK) pos_consec = __all_sync(0xffffffffu, rb.valid && rb.cell == __shfl_sync(0xffffffffu, rb.cell, 0) + lane);
+        if (lane == 0) {  // one lane, one branch level (bulk instructions issue through uniform registers)
+          if (cnt > 0) {
+            bulk_prefetch_l2(P.pts + Pa * DIM, (uint32_t)(cnt * DIM * 8));
+            bulk_prefetch_l2(P.w + Pa, (uint32_t)(cnt * 8));
+            if constexpr (T::NEED_NORMAL) bulk_prefetch_l2(P.normals + Pa * DIM, (uint32_t)(cnt * DIM * 8));
+          }
+          if constexpr (POS_BULK)
+            if (pos_consec) bulk_prefetch_l2(P.elem_pos + (int64_t)rb.cell * Meta::NPOS, CB * Meta::NPOS);
+        }
+      }
+#endif
       if (rb.t >= 0 && rb.valid) {
         const int32_t cell = rb.cell;
         if constexpr (DIM == 2) {
@@ -537,7 +561,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
 #pragma unroll
             for (int p = 0; p < Pn; ++p)
 #pragma unroll
-              for (int q = 0; q < Pn; ++q) mu[p][q] = M.mu[p * Pn + q][lane];
+              for (int q = 0; q < Pn; ++q) mu[p][q] = M.mu[lane][p * Pn + q];
             static_for<0, NXW>([&](auto XW) {
               if (xw == decltype(XW)::value) moment_expand<T, 1, CB, decltype(XW)::value, NXW>(P, M, lane, 0, mu);
             });
