@@ -33,10 +33,17 @@ class QuadratureDesc(C.Structure):
 
 class CsrDesc(C.Structure):
     _fields_ = [("num_rows", C.c_int64), ("nnz", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p),
-                ("peer_row0", C.c_int64), ("peer_rowstart", C.c_void_p)]  # fmt: skip
+                ("peer_row0", C.c_int64), ("peer_rowstart", C.c_void_p), ("flags", C.c_int32), ("pad_", C.c_int32)]  # fmt: skip
 
-    def __init__(self, num_rows=0, nnz=0, indptr=None, indices=None, values=None, peer_row0=None, peer_rowstart=None):
-        super().__init__(num_rows, nnz, indptr, indices, values, num_rows if peer_row0 is None else peer_row0, peer_rowstart)
+    def __init__(self, num_rows=0, nnz=0, indptr=None, indices=None, values=None, peer_row0=None, peer_rowstart=None, flags=0):
+        super().__init__(num_rows, nnz, indptr, indices, values, num_rows if peer_row0 is None else peer_row0, peer_rowstart, flags, 0)
+
+
+CQ_CSR_PEER_TARGET = 1
+
+
+class MatrixJob(C.Structure):
+    _fields_ = [("form", C.POINTER(FormDesc)), ("space", C.POINTER(SpaceDesc)), ("A", C.POINTER(CsrDesc)), ("values_host", C.c_void_p)]
 
 
 class CircleDesc(C.Structure):
@@ -90,6 +97,16 @@ _SIGNATURES = {
     "cq_assemble_matrix_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
     "cq_assemble_vector_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_assemble_scalar_host": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
+    "cq_assemble_matrices_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(MatrixJob), C.POINTER(MeshDesc), C.POINTER(QuadratureDesc), C.c_void_p]),
+    "cq_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "cq_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cq_comm_destroy": (C.c_int, [C.c_void_p]),
+    "cq_exchange_offrank": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cq_exchange_offrank_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    "cq_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cq_peer_flags": (C.c_void_p, [C.c_void_p]),
+    "cq_peer_fence_setup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_peer_fence": (C.c_int, [C.c_void_p, C.c_void_p]),
 }  # fmt: skip
 
 

@@ -182,15 +182,22 @@ def create_matrix(form: Form, pattern_cells=None, zero: bool = True) -> CSRMatri
 
 def _csr_desc(A: CSRMatrix):
     return _lib.CsrDesc(A.shape[0], A.nnz, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data),
-                        getattr(A, "peer_row0", None), _ptr(getattr(A, "peer_rowstart", None)))
+                        getattr(A, "peer_row0", None), _ptr(getattr(A, "peer_rowstart", None)),
+                        _lib.CQ_CSR_PEER_TARGET if getattr(A, "peer_target", False) else 0)
 
 
 def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: str = "form", zero: bool | None = None) -> CSRMatrix:
     """reference customquad/assemble_matrix.py:10-47.  Returns the (device) CSR matrix; like the
     reference's PETSc Mat it is "unassembled" until ``A.assemble()``.
 
-    ``zero``: A.zeroEntries() (:20) as part of the call -- the first integral runs cq_assemble_matrix_zero, which
-    zeroes inside the assembly kernel.  Default: True for a matrix created here, False (accumulate) for a given A."""
+    ``zero``: A.zeroEntries() (:20) as part of the call -- the first integral runs cq_assemble_matrix_zero (memset +
+    kernel, or zeroing inside the kernel with ``set_fused_zero``).  Default: True for a matrix created here, False
+    (accumulate) for a given A.
+
+    Multi-GPU: a matrix whose rows receive a neighbour rank's peer scatter (``SlabExchange.enable_peer_scatter``; the
+    neighbour's kernels add into it over NVLink at any time between two fences) is zeroed with the protocol
+    zero -> fence -> assemble; the caller completes it with ``exchange_matrix`` (the second fence) before reading.
+    Every rank has to make the same calls in the same order."""
     assert form.rank == 2
     L = _lib.load()
     dev = _dev()
@@ -203,6 +210,11 @@ def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: st
         zero = True if zero is None else zero
         A = create_matrix(form, cells, zero=not zero)
     csr = _csr_desc(A)
+    if zero and getattr(A, "peer_exchange", None) is not None:
+        # peer scatter (either side): the zeroing of every rank's matrix must be complete before any rank's kernel adds
+        A.data.zero_()
+        A.peer_exchange.fence(dev)
+        zero = False
     if zero and not ids:
         A.data.zero_()
     for i, _id in enumerate(ids):  # qr tuples are matched to integrals by position (:26,42)
@@ -281,6 +293,23 @@ def assemble_matrix_host(form: Form, q: RaggedQuadrature, A: CSRMatrix, values_h
     csr = _csr_desc(A)
     vh = C.c_void_p(values_host.ctypes.data if isinstance(values_host, np.ndarray) else values_host.data_ptr())
     _lib.check(L.cq_assemble_matrix_host(_lib.ctx(dev.index), C.byref(c.form), C.byref(c.mesh), c.space_ref(), C.byref(c.qr), C.byref(csr), vh, _stream_ptr()))
+
+
+def assemble_matrices_host(forms, q: RaggedQuadrature, mats, values_host) -> None:
+    """cq_assemble_matrices_host: several bilinear forms over ONE qr tuple in host memory (the reference's demo
+    integrates its bulk rule into a matrix and a vector, demo/poisson.py:193,209).  The rule crosses PCIe once; every
+    matrix is zeroed, assembled and copied to its host buffer (``values_host[j]``, or None to keep it on the device)."""
+    L = _lib.load()
+    dev = _dev()
+    calls = [_Call(f, q, dev, host_qr=True, A=A) for f, A in zip(forms, mats)]
+    csrs = [_csr_desc(A) for A in mats]
+    jobs = (_lib.MatrixJob * len(calls))()
+    for j, (c, csr, vh) in enumerate(zip(calls, csrs, values_host)):
+        jobs[j].form = C.pointer(c.form)
+        jobs[j].space = C.pointer(c.space)
+        jobs[j].A = C.pointer(csr)
+        jobs[j].values_host = None if vh is None else (vh.ctypes.data if isinstance(vh, np.ndarray) else vh.data_ptr())
+    _lib.check(L.cq_assemble_matrices_host(_lib.ctx(dev.index), len(calls), jobs, C.byref(calls[0].mesh), C.byref(calls[0].qr), _stream_ptr()))
 
 
 def assemble_vector_host(form: Form, q: RaggedQuadrature, b: Vector, b_host) -> None:

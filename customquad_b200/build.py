@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcq_b200.so")
-SOURCES = ["cq_api.cu", "cq_launch_matrix.cu", "cq_launch_vector.cu", "cq_launch_scalar.cu", "cq_staged.cu"]
+SOURCES = ["cq_api.cu", "cq_comm.cu", "cq_launch_matrix.cu", "cq_launch_vector.cu", "cq_launch_scalar.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"])
+        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-ldl"])
     return LIB
 
 

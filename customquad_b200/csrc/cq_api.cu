@@ -263,9 +263,9 @@ int cq_ctx_create(int device, cq_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->coop_launch = prop.cooperativeLaunch;
-  c->fused_zero = getenv("CQ_ZERO_FUSED") ? atoi(getenv("CQ_ZERO_FUSED")) != 0 : 0;
-  int rc = check_cuda(cudaMalloc(&c->err_flag, sizeof(int)), "cudaMalloc(err_flag)");
-  if (!rc) rc = check_cuda(cudaMemset(c->err_flag, 0, sizeof(int)), "cudaMemset(err_flag)");
+  c->fused_zero = 0;
+  int rc = check_cuda(cudaMalloc(&c->err_flag, 2 * sizeof(int)), "cudaMalloc(err_flag)");
+  if (!rc) rc = check_cuda(cudaMemset(c->err_flag, 0, 2 * sizeof(int)), "cudaMemset(err_flag)");
   if (!rc) rc = check_cuda(cudaMalloc(&c->work_counter, sizeof(unsigned int)), "cudaMalloc(work_counter)");
   if (!rc) rc = check_cuda(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), "cudaDeviceGetAttribute");
   if (!rc) rc = check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -284,6 +284,7 @@ int cq_ctx_create(int device, cq_ctx** out) {
 int cq_ctx_destroy(cq_ctx* ctx) {
   if (!ctx) return CQ_OK;
   cudaSetDevice(ctx->device);
+  comm_release(ctx);
   if (ctx->err_flag) cudaFree(ctx->err_flag);
   if (ctx->work_counter) cudaFree(ctx->work_counter);
   if (ctx->stage) cudaFree(ctx->stage);
@@ -333,6 +334,10 @@ static int assemble_matrix_impl(cq_ctx* ctx, const cq_form_desc* form, const cq_
   if (int rc = set_device(ctx)) return rc;
   if (qr->num_entries == 0)
     return zero_first ? check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * (size_t)A->nnz, static_cast<cudaStream_t>(stream)), "zeroEntries") : CQ_OK;
+  if (zero_first && (A->flags & CQ_CSR_PEER_TARGET)) {
+    set_error("this matrix receives a neighbour rank's peer scatter: zero it, fence, then assemble (cq_peer_fence / SlabExchange.fence)");
+    return CQ_ERR_UNSUPPORTED;
+  }
   P.zero_req = zero_first ? 1 : 0;
   P.nnz = A->nnz;
   P.indptr = A->indptr; P.indices = A->indices; P.values = A->values;
@@ -415,15 +420,14 @@ int cq_mesh_classify(cq_ctx* ctx, int cell_type, const cq_mesh* mesh, int32_t* f
   P.geom_dofmap = mesh->geom_dofmap;
   P.coords = mesh->coords;
   int one = 1;
-  // the error flag doubles as the scratch word (it is 0 between calls; restored below)
-  if (int rc = check_cuda(cudaMemcpyAsync(ctx->err_flag, &one, sizeof(int), cudaMemcpyHostToDevice, s), "flag init")) return rc;
+  int* scratch = ctx->err_flag + 1;  // own word: a pending sparsity violation in err_flag[0] survives this call
+  if (int rc = check_cuda(cudaMemcpyAsync(scratch, &one, sizeof(int), cudaMemcpyHostToDevice, s), "flag init")) return rc;
   const int grid = (int)((mesh->num_cells + 255) / 256 < (int64_t)ctx->num_sms * 8 ? (mesh->num_cells + 255) / 256 : (int64_t)ctx->num_sms * 8);
-  if (cell_type == CQ_CELL_QUADRILATERAL) classify_kernel<2><<<grid, 256, 0, s>>>(P, mesh->num_cells, ctx->err_flag);
-  else classify_kernel<3><<<grid, 256, 0, s>>>(P, mesh->num_cells, ctx->err_flag);
+  if (cell_type == CQ_CELL_QUADRILATERAL) classify_kernel<2><<<grid, 256, 0, s>>>(P, mesh->num_cells, scratch);
+  else classify_kernel<3><<<grid, 256, 0, s>>>(P, mesh->num_cells, scratch);
   ctx->launches++;
   if (int rc = check_cuda(cudaGetLastError(), "classify_kernel launch")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "flag D2H")) return rc;
-  if (int rc = check_cuda(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s), "flag reset")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, scratch, sizeof(int), cudaMemcpyDeviceToHost, s), "flag D2H")) return rc;
   if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
   if (*ctx->host_flag) *flags |= CQ_MESH_AXIS_ALIGNED;
   return CQ_OK;
@@ -448,12 +452,13 @@ int cq_build_scatter_map(cq_ctx* ctx, int cell_type, int degree, int bs, int64_t
   if (int rc = check_cuda(cudaMemsetAsync(out, 0, (size_t)num_cells * stride, s), "memset map")) return rc;
   const int64_t total = num_cells * n * n;
   const int grid = (int)((total + 255) / 256 < (int64_t)ctx->num_sms * 16 ? (total + 255) / 256 : (int64_t)ctx->num_sms * 16);
-  scatter_map_kernel<<<grid, 256, 0, s>>>(dofmap, num_cells, n, stride, bs, A->indptr, A->indices, out, ctx->err_flag);
+  int* scratch = ctx->err_flag + 1;  // own word (see cq_mesh_classify)
+  if (int rc = check_cuda(cudaMemsetAsync(scratch, 0, sizeof(int), s), "scratch reset")) return rc;
+  scatter_map_kernel<<<grid, 256, 0, s>>>(dofmap, num_cells, n, stride, bs, A->indptr, A->indices, out, scratch);
   ctx->launches++;
   if (int rc = check_cuda(cudaGetLastError(), "scatter_map_kernel launch")) return rc;
   // setup call: synchronous check so the caller knows whether the map is usable
-  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "err_flag D2H")) return rc;
-  if (int rc = check_cuda(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s), "err_flag reset")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(ctx->host_flag, scratch, sizeof(int), cudaMemcpyDeviceToHost, s), "scratch D2H")) return rc;
   if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
   if (*ctx->host_flag == 1) { set_error("scatter map: a (row, col) of the dofmap is absent from the CSR pattern"); return CQ_ERR_SPARSITY; }
   if (*ctx->host_flag == 2) { set_error("scatter map: a row holds more than 255 scalar entries"); return CQ_ERR_UNSUPPORTED; }
@@ -604,7 +609,7 @@ int cq_axpy(cq_ctx* ctx, int64_t n, const double* x, double* y, void* stream) {
 
 // ---------------------------------------------------------------------------------------------
 // End-to-end entry points: qr data in host memory.  The ragged arrays are streamed to the device
-// in chunks of entries on ctx->copy_stream; the kernel for chunk c runs on `stream` as soon as its
+// in chunks of entries on ctx->copy_stream; the kernels for chunk c run on `stream` as soon as its
 // copy has landed, overlapping with the copy of chunk c+1.  Because every kernel accumulates into
 // the same sink (ADD_VALUES), chunking does not change the result.
 // ---------------------------------------------------------------------------------------------
@@ -620,14 +625,27 @@ static int ensure_stage(cq_ctx* ctx, size_t bytes) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int no_after_chunk(int, int, const int64_t*) { return CQ_OK; }
+static int no_after_chunk(int, int) { return CQ_OK; }
 
-// rows_back: also work out val_lo[c] (see cq_assemble_matrix_host) before the first chunk is launched
+constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_HOST_JOBS = 8;
+
+// What the chunk loop needs to know about a matrix whose finished rows go back early (see cq_assemble_matrices_host)
+struct RowsBack {
+  int n = 0;            // scalar dofs per cell of the job's space
+  int bs = 1;
+  const int32_t* dofmap = nullptr;
+  const cq_csr* A = nullptr;
+  int64_t val_lo[MAX_CHUNKS + 1] = {};  // out: CSR offset of the smallest row any chunk >= c touches
+};
+
+// launch(qc): enqueue the kernels of one chunk on `s`; after(c, nchunks): whatever follows chunk c.
+// rb[0..nrb): matrices for which val_lo is worked out before the first chunk is launched.
 template <class LaunchFn, class AfterFn>
-static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* /*mesh*/, const cq_space* space, const cq_csr* A,
-                            const cq_quadrature* qh, cudaStream_t s, bool rows_back, LaunchFn&& launch, AfterFn&& after) {
-  if (!ctx || !form || !qh) { set_error("null argument"); return CQ_ERR_INVALID; }
-  const int gdim = gdim_of(form->cell_type);
+static int run_host_chunked(cq_ctx* ctx, const int cell_type, const cq_quadrature* qh, cudaStream_t s, RowsBack* rb, const int nrb,
+                            LaunchFn&& launch, AfterFn&& after) {
+  if (!ctx || !qh) { set_error("null argument"); return CQ_ERR_INVALID; }
+  const int gdim = gdim_of(cell_type);
   const int64_t C = qh->num_entries, Pn = qh->num_points;
   if (C == 0) return CQ_OK;
   if (!qh->cells || !qh->offsets || (Pn > 0 && (!qh->pts || !qh->weights))) { set_error("qr host arrays null"); return CQ_ERR_INVALID; }
@@ -652,42 +670,45 @@ static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
   if (int rc = check_cuda(cudaEventRecord(ctx->ev[11], s), "cudaEventRecord")) return rc;
   if (int rc = check_cuda(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[11], 0), "cudaStreamWaitEvent")) return rc;
 
-  const int nchunks = C >= (1 << 16) ? 8 : 1;
-  int64_t val_lo[17];
-  for (int c = 0; c <= nchunks; ++c) val_lo[c] = 0;
-  if (rows_back && nchunks > 1 && space && space->dofmap && A && A->indptr) {
-    // all cell ids first (small), then the per-chunk smallest row and its CSR offset
-    cudaStream_t cs = ctx->copy_stream;
+  const int nchunks = C >= (1 << 16) ? MAX_CHUNKS : 1;
+  cudaStream_t cs = ctx->copy_stream;
+  bool cells_up = false;
+  if (nchunks > 1 && nrb > 0) {
+    // all cell ids first (small), then per matrix the smallest row of every chunk and its CSR offset
     int rc = check_cuda(cudaMemcpyAsync(const_cast<int32_t*>(qd.cells), qh->cells, sizeof(int32_t) * C, cudaMemcpyHostToDevice, cs), "H2D cells");
-    if (!rc) rc = check_cuda(cudaMemsetAsync(ctx->chunk_rowmin, 0x7f, 16 * sizeof(int32_t), cs), "rowmin init");
     if (rc) return rc;
-    int n = form->degree + 1;
-    n = gdim == 2 ? n * n : n * n * n;
-    chunk_rowmin_kernel<<<ctx->num_sms * 4, 256, 0, cs>>>(qd.cells, C, nchunks, space->dofmap, n, form->bs, ctx->chunk_rowmin);
-    ctx->launches++;
-    rc = check_cuda(cudaGetLastError(), "chunk_rowmin_kernel launch");
-    if (!rc) rc = check_cuda(cudaMemcpyAsync(ctx->host_rowmin, ctx->chunk_rowmin, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, cs), "rowmin D2H");
-    if (!rc) rc = check_cuda(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
-    if (rc) return rc;
-    int32_t suffix = 0x7fffffff;
-    for (int c = nchunks - 1; c >= 0; --c) {
-      if (ctx->host_rowmin[c] < suffix) suffix = ctx->host_rowmin[c];
-      ctx->host_rowmin[c] = suffix;
+    cells_up = true;
+    for (int j = 0; j < nrb; ++j) {
+      RowsBack& R = rb[j];
+      rc = check_cuda(cudaMemsetAsync(ctx->chunk_rowmin, 0x7f, 16 * sizeof(int32_t), cs), "rowmin init");
+      if (rc) return rc;
+      chunk_rowmin_kernel<<<ctx->num_sms * 4, 256, 0, cs>>>(qd.cells, C, nchunks, R.dofmap, R.n, R.bs, ctx->chunk_rowmin);
+      ctx->launches++;
+      rc = check_cuda(cudaGetLastError(), "chunk_rowmin_kernel launch");
+      if (!rc) rc = check_cuda(cudaMemcpyAsync(ctx->host_rowmin, ctx->chunk_rowmin, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, cs), "rowmin D2H");
+      if (!rc) rc = check_cuda(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
+      if (rc) return rc;
+      int32_t suffix = 0x7fffffff;
+      for (int c = nchunks - 1; c >= 0; --c) {
+        if (ctx->host_rowmin[c] < suffix) suffix = ctx->host_rowmin[c];
+        ctx->host_rowmin[c] = suffix;
+      }
+      for (int c = 0; c < nchunks && !rc; ++c) {
+        const int64_t row = ctx->host_rowmin[c] < R.A->num_rows ? ctx->host_rowmin[c] : R.A->num_rows;
+        rc = check_cuda(cudaMemcpyAsync(ctx->host_vallo + c, R.A->indptr + row, sizeof(int64_t), cudaMemcpyDeviceToHost, cs), "indptr D2H");
+      }
+      if (!rc) rc = check_cuda(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
+      if (rc) return rc;
+      for (int c = 0; c < nchunks; ++c) R.val_lo[c] = ctx->host_vallo[c];
+      R.val_lo[nchunks] = R.A->nnz;
     }
-    for (int c = 0; c < nchunks && !rc; ++c) {
-      const int64_t row = ctx->host_rowmin[c] < A->num_rows ? ctx->host_rowmin[c] : A->num_rows;
-      rc = check_cuda(cudaMemcpyAsync(ctx->host_vallo + c, A->indptr + row, sizeof(int64_t), cudaMemcpyDeviceToHost, cs), "indptr D2H");
-    }
-    if (!rc) rc = check_cuda(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
-    if (rc) return rc;
-    for (int c = 0; c < nchunks; ++c) val_lo[c] = ctx->host_vallo[c];
   }
   for (int c = 0; c < nchunks; ++c) {
     const int64_t k0 = C * c / nchunks, k1 = C * (c + 1) / nchunks;
     if (k1 == k0) continue;
     const int64_t p0 = qh->offsets[k0], p1 = qh->offsets[k1];
-    cudaStream_t cs = ctx->copy_stream;
-    int rc = check_cuda(cudaMemcpyAsync(const_cast<int32_t*>(qd.cells) + k0, qh->cells + k0, sizeof(int32_t) * (k1 - k0), cudaMemcpyHostToDevice, cs), "H2D cells");
+    int rc = CQ_OK;
+    if (!cells_up) rc = check_cuda(cudaMemcpyAsync(const_cast<int32_t*>(qd.cells) + k0, qh->cells + k0, sizeof(int32_t) * (k1 - k0), cudaMemcpyHostToDevice, cs), "H2D cells");
     if (!rc) rc = check_cuda(cudaMemcpyAsync(const_cast<int64_t*>(qd.offsets) + k0, qh->offsets + k0, sizeof(int64_t) * (k1 - k0 + 1), cudaMemcpyHostToDevice, cs), "H2D offsets");
     if (!rc && p1 > p0) {
       rc = check_cuda(cudaMemcpyAsync(const_cast<double*>(qd.pts) + gdim * p0, qh->pts + gdim * p0, sizeof(double) * gdim * (p1 - p0), cudaMemcpyHostToDevice, cs), "H2D pts");
@@ -703,51 +724,92 @@ static int run_host_chunked(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
     qc.offsets = qd.offsets + k0;
     qc.num_entries = k1 - k0;
     if (int lrc = launch(qc)) return lrc;
-    if (int arc = after(c, nchunks, val_lo)) return arc;
+    if (int arc = after(c, nchunks)) return arc;
   }
   return CQ_OK;
 }
 
 extern "C" {
 
-int cq_assemble_matrix_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
-                            const cq_quadrature* qr_host, const cq_csr* A, double* values_host, void* stream) {
-  if (!A || !A->values) { set_error("CSR null"); return CQ_ERR_INVALID; }
+int cq_assemble_matrices_host(cq_ctx* ctx, int njobs, const cq_matrix_job* jobs, const cq_mesh* mesh, const cq_quadrature* qr_host,
+                              void* stream) {
+  if (!ctx || !jobs || !mesh || !qr_host || njobs < 1 || njobs > MAX_HOST_JOBS) { set_error("bad argument (1..%d jobs)", MAX_HOST_JOBS); return CQ_ERR_INVALID; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ctx) cudaSetDevice(ctx->device);
-  if (int rc = check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * A->nnz, s), "zeroEntries")) return rc;  // A.zeroEntries()
+  if (int rc = set_device(ctx)) return rc;
+  RowsBack rb[MAX_HOST_JOBS];
+  int rb_of[MAX_HOST_JOBS];
+  int64_t copied[MAX_HOST_JOBS] = {};
+  int nrb = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const cq_matrix_job& J = jobs[j];
+    if (!J.form || !J.space || !J.A || !J.A->values || !J.A->indptr) { set_error("job %d: null form / space / CSR", j); return CQ_ERR_INVALID; }
+    if (J.form->cell_type != jobs[0].form->cell_type) { set_error("jobs on different cell types"); return CQ_ERR_INVALID; }
+    if (J.A->flags & CQ_CSR_PEER_TARGET) { set_error("job %d: the matrix is the target of a neighbour's peer scatter (cq_csr.flags)", j); return CQ_ERR_UNSUPPORTED; }
+    if (int rc = check_cuda(cudaMemsetAsync(J.A->values, 0, sizeof(double) * (size_t)J.A->nnz, s), "zeroEntries")) return rc;  // A.zeroEntries()
+    rb_of[j] = -1;
+    if (J.values_host && J.space->dofmap) {
+      int n = J.form->degree + 1;
+      n = gdim_of(J.form->cell_type) == 2 ? n * n : n * n * n;
+      rb[nrb].n = n;
+      rb[nrb].bs = J.form->bs;
+      rb[nrb].dofmap = J.space->dofmap;
+      rb[nrb].A = J.A;
+      rb_of[j] = nrb++;
+    }
+  }
   // Rows are final once no later chunk touches them: values below val_lo[c + 1] (the CSR offset of the smallest row
   // any chunk after c touches) go back to the host on a second stream while the points of the later chunks are still
   // coming in (PCIe is full duplex).  For a sorted cell list with a locality-preserving dof numbering that hides all
-  // but the last chunk's rows; for an arbitrary list val_lo is 0 and everything is copied at the end, as before.
-  int64_t copied = 0;
-  auto after_chunk = [&](int c, int nchunks, const int64_t* val_lo) -> int {
-    if (!values_host || c + 1 >= nchunks) return CQ_OK;
-    const int64_t upto = val_lo[c + 1];
-    if (upto <= copied) return CQ_OK;
-    int rc = check_cuda(cudaEventRecord(ctx->kev[c], s), "cudaEventRecord");
-    if (!rc) rc = check_cuda(cudaStreamWaitEvent(ctx->d2h_stream, ctx->kev[c], 0), "cudaStreamWaitEvent");
-    if (!rc) rc = check_cuda(cudaMemcpyAsync(values_host + copied, A->values + copied, sizeof(double) * (upto - copied), cudaMemcpyDeviceToHost, ctx->d2h_stream), "D2H rows");
-    copied = upto;
-    return rc;
+  // but the last chunk's rows; for an arbitrary list val_lo is 0 and everything is copied at the end.
+  auto after_chunk = [&](int c, int nchunks) -> int {
+    if (c + 1 >= nchunks) return CQ_OK;
+    bool recorded = false;
+    for (int j = 0; j < njobs; ++j) {
+      if (rb_of[j] < 0) continue;
+      const int64_t upto = rb[rb_of[j]].val_lo[c + 1];
+      if (upto <= copied[j]) continue;
+      int rc = CQ_OK;
+      if (!recorded) {
+        rc = check_cuda(cudaEventRecord(ctx->kev[c], s), "cudaEventRecord");
+        if (!rc) rc = check_cuda(cudaStreamWaitEvent(ctx->d2h_stream, ctx->kev[c], 0), "cudaStreamWaitEvent");
+        recorded = true;
+      }
+      if (!rc) rc = check_cuda(cudaMemcpyAsync(jobs[j].values_host + copied[j], jobs[j].A->values + copied[j], sizeof(double) * (upto - copied[j]), cudaMemcpyDeviceToHost, ctx->d2h_stream), "D2H rows");
+      if (rc) return rc;
+      copied[j] = upto;
+    }
+    return CQ_OK;
   };
-  int rc = run_host_chunked(ctx, form, mesh, space, A, qr_host, s, values_host != nullptr,
-                            [&](const cq_quadrature& qc) { return cq_assemble_matrix(ctx, form, mesh, space, &qc, A, stream); }, after_chunk);
-  if (rc) return rc;
-  if (values_host && A->nnz > copied)
-    if (int rc2 = check_cuda(cudaMemcpyAsync(values_host + copied, A->values + copied, sizeof(double) * (A->nnz - copied), cudaMemcpyDeviceToHost, s), "D2H values")) return rc2;
-  if (int rc2 = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc2;
+  auto launch = [&](const cq_quadrature& qc) -> int {
+    for (int j = 0; j < njobs; ++j)
+      if (int rc = cq_assemble_matrix(ctx, jobs[j].form, mesh, jobs[j].space, &qc, jobs[j].A, stream)) return rc;
+    return CQ_OK;
+  };
+  if (int rc = run_host_chunked(ctx, jobs[0].form->cell_type, qr_host, s, rb, nrb, launch, after_chunk)) return rc;
+  // the rest: after the last kernel, on the result stream (keeps the order of the host buffer writes simple)
+  if (int rc = check_cuda(cudaEventRecord(ctx->kev[15], s), "cudaEventRecord")) return rc;
+  if (int rc = check_cuda(cudaStreamWaitEvent(ctx->d2h_stream, ctx->kev[15], 0), "cudaStreamWaitEvent")) return rc;
+  for (int j = 0; j < njobs; ++j)
+    if (jobs[j].values_host && jobs[j].A->nnz > copied[j])
+      if (int rc = check_cuda(cudaMemcpyAsync(jobs[j].values_host + copied[j], jobs[j].A->values + copied[j], sizeof(double) * (jobs[j].A->nnz - copied[j]), cudaMemcpyDeviceToHost, ctx->d2h_stream), "D2H values")) return rc;
+  if (int rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize")) return rc;
   return check_cuda(cudaStreamSynchronize(ctx->d2h_stream), "cudaStreamSynchronize(d2h)");
+}
+
+int cq_assemble_matrix_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
+                            const cq_quadrature* qr_host, const cq_csr* A, double* values_host, void* stream) {
+  const cq_matrix_job job = {form, space, A, values_host};
+  return cq_assemble_matrices_host(ctx, 1, &job, mesh, qr_host, stream);
 }
 
 int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
                             const cq_quadrature* qr_host, double* b_dev, double* b_host, void* stream) {
-  if (!b_dev || !space) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (!ctx || !form || !b_dev || !space) { set_error("null argument"); return CQ_ERR_INVALID; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ctx) cudaSetDevice(ctx->device);
-  const size_t bytes = sizeof(double) * space->num_dofs * (form ? form->bs : 1);
+  if (int rc = set_device(ctx)) return rc;
+  const size_t bytes = sizeof(double) * space->num_dofs * form->bs;
   if (int rc = check_cuda(cudaMemsetAsync(b_dev, 0, bytes, s), "zero b")) return rc;
-  int rc = run_host_chunked(ctx, form, mesh, space, nullptr, qr_host, s, false,
+  int rc = run_host_chunked(ctx, form->cell_type, qr_host, s, nullptr, 0,
                             [&](const cq_quadrature& qc) { return cq_assemble_vector(ctx, form, mesh, space, &qc, b_dev, stream); }, no_after_chunk);
   if (rc) return rc;
   if (b_host)
@@ -757,14 +819,14 @@ int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
 
 int cq_assemble_scalar_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh, const cq_space* space,
                             const cq_quadrature* qr_host, double* m_host, void* stream) {
-  if (!ctx || !m_host) { set_error("null argument"); return CQ_ERR_INVALID; }
+  if (!ctx || !form || !m_host) { set_error("null argument"); return CQ_ERR_INVALID; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaSetDevice(ctx->device);
+  if (int rc = set_device(ctx)) return rc;
   if (!ctx->scalar_dev)
     if (int rc = check_cuda(cudaMalloc(&ctx->scalar_dev, sizeof(double)), "cudaMalloc(m)")) return rc;
   double* m_dev = ctx->scalar_dev;
   if (int rc = check_cuda(cudaMemsetAsync(m_dev, 0, sizeof(double), s), "zero m")) return rc;
-  int rc = run_host_chunked(ctx, form, mesh, space, nullptr, qr_host, s, false,
+  int rc = run_host_chunked(ctx, form->cell_type, qr_host, s, nullptr, 0,
                             [&](const cq_quadrature& qc) { return cq_assemble_scalar(ctx, form, mesh, space, &qc, m_dev, stream); }, no_after_chunk);
   if (rc) return rc;
   if (int rc2 = check_cuda(cudaMemcpyAsync(m_host, m_dev, sizeof(double), cudaMemcpyDeviceToHost, s), "D2H m")) return rc2;

@@ -288,9 +288,9 @@ CQ_DEVINL void eval_fn(const double* __restrict__ p, int a, const double (&x)[DI
 // ---------------------------------------------------------------------------------------------
 CQ_DEVINL void red_add_f64(double* addr, double v) {
   // REDG.E.ADD.F64.RN.STRONG.GPU: fire-and-forget FP64 reduction at L2 (no return value)
-#if defined(CQ_EXPERIMENT_NORED)  // profiling builds only (profiles/build_variant.sh): value is formed, RED never issues
+#if defined(CQ_PROFILING) && defined(CQ_EXPERIMENT_NORED)  // profiling builds only (profiles/build_variant.sh): value is formed, RED never issues
   if (v == 1.2345e300) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-#elif defined(CQ_EXPERIMENT_ST)   // profiling builds only: plain store instead of the reduction (wrong results)
+#elif defined(CQ_PROFILING) && defined(CQ_EXPERIMENT_ST)   // profiling builds only: plain store instead of the reduction (wrong results)
   asm volatile("st.global.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 #else
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");

@@ -196,13 +196,7 @@ __global__ void __launch_bounds__(THREADS) assemble_q2hex_dmma_kernel(const KPar
 
   int lat[4][3];
   bool valid[4];
-#pragma unroll
-  for (int tile = 0; tile < 4; ++tile) {
-    const int j = 8 * tile + g;
-    const int pk = c_q2hex_lat[j];
-    lat[tile][0] = pk & 3; lat[tile][1] = (pk >> 2) & 3; lat[tile][2] = (pk >> 4) & 3;
-    valid[tile] = j < N;
-  }
+  dmma_lane_dofs(g, lat, valid);
 
   for (int64_t k = warp_id; k < P.num_entries; k += num_warps) {
     const int32_t cell = __ldg(P.cells + k);
@@ -215,98 +209,8 @@ __global__ void __launch_bounds__(THREADS) assemble_q2hex_dmma_kernel(const KPar
     const double gamma = FORM == CQ_FORM_NITSCHE ? P.betaN / geo.hK : 0.0;
 
     double D[10][2];  // upper-triangular tiles (ti <= tj), row-major enumeration
-#pragma unroll
-    for (int i = 0; i < 10; ++i) D[i][0] = D[i][1] = 0.0;
-
-    for (int64_t qb = q0; qb < q1; qb += 4) {
-      const int64_t q = qb + t;
-      const bool live = q < q1;
-      double xi[3] = {0.5, 0.5, 0.5}, nrm[3] = {0.0, 0.0, 0.0}, w = 0.0;
-      if (live) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) xi[d] = __ldg(P.pts + 3 * q + d);
-        w = __ldg(P.w + q);
-        if constexpr (FORM == CQ_FORM_NITSCHE)
-#pragma unroll
-          for (int d = 0; d < 3; ++d) nrm[d] = __ldg(P.normals + 3 * q + d);
-      }
-      const Basis1D<2> b0(xi[0]), b1(xi[1]), b2(xi[2]);
-      double adj[3][3], det;
-      if (geo.affine) {  // constant Jacobian: per-cell values
-        det = geo.det0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int b = 0; b < 3; ++b) adj[a][b] = geo.adj0[a][b];
-      } else {
-        double J[3][3];
-        geo.jacobian(xi, J);
-        det = det_adj<3>(J, adj);
-      }
-      const double adet = fabs(det);
-
-      if constexpr (FORM == CQ_FORM_MASS) {
-        const double s = w * adet;
-        double f[4], sf[4];
-#pragma unroll
-        for (int tile = 0; tile < 4; ++tile) {
-          const double v = sel3(b0.v, lat[tile][0]) * sel3(b1.v, lat[tile][1]) * sel3(b2.v, lat[tile][2]);
-          f[tile] = valid[tile] ? v : 0.0;
-          sf[tile] = s * f[tile];
-        }
-        int e = 0;
-#pragma unroll
-        for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-          for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], sf[ti], f[tj]);
-      } else if constexpr (FORM == CQ_FORM_STIFFNESS) {
-        const double sc = w / adet;
-        double f[4][3], sf[4][3];
-#pragma unroll
-        for (int tile = 0; tile < 4; ++tile) {
-          const double v0 = sel3(b0.v, lat[tile][0]), v1 = sel3(b1.v, lat[tile][1]), v2 = sel3(b2.v, lat[tile][2]);
-          const double d0 = sel3(b0.d, lat[tile][0]), d1 = sel3(b1.d, lat[tile][1]), d2 = sel3(b2.d, lat[tile][2]);
-          const double gr[3] = {d0 * v1 * v2, v0 * d1 * v2, v0 * v1 * d2};
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const double a = fma(adj[2][c], gr[2], fma(adj[1][c], gr[1], adj[0][c] * gr[0]));
-            f[tile][c] = valid[tile] ? a : 0.0;
-            sf[tile][c] = sc * f[tile][c];
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          int e = 0;
-#pragma unroll
-          for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-            for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], sf[ti][c], f[tj][c]);
-        }
-      } else {  // CQ_FORM_NITSCHE:  psi_i u_j - e_i psi_j,  e = s dn,  u = s gamma psi - e
-        const double s = w * adet, sg = s * gamma, inv_det = 1.0 / det;
-        double m[3];
-#pragma unroll
-        for (int e = 0; e < 3; ++e) m[e] = fma(adj[e][2], nrm[2], fma(adj[e][1], nrm[1], adj[e][0] * nrm[0])) * inv_det;
-        double psi[4], ev[4], uv[4];
-#pragma unroll
-        for (int tile = 0; tile < 4; ++tile) {
-          const double v0 = sel3(b0.v, lat[tile][0]), v1 = sel3(b1.v, lat[tile][1]), v2 = sel3(b2.v, lat[tile][2]);
-          const double d0 = sel3(b0.d, lat[tile][0]), d1 = sel3(b1.d, lat[tile][1]), d2 = sel3(b2.d, lat[tile][2]);
-          const double dn = fma(m[2], v0 * v1 * d2, fma(m[1], v0 * d1 * v2, m[0] * (d0 * v1 * v2)));
-          psi[tile] = valid[tile] ? v0 * v1 * v2 : 0.0;
-          ev[tile] = valid[tile] ? s * dn : 0.0;
-          uv[tile] = fma(sg, psi[tile], -ev[tile]);
-        }
-        int e = 0;
-#pragma unroll
-        for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-          for (int tj = ti; tj < 4; ++tj, ++e) {
-            dmma_m8n8k4(D[e], psi[ti], uv[tj]);
-            dmma_m8n8k4(D[e], -ev[ti], psi[tj]);
-          }
-      }
-    }
+    dmma_cell_tiles<FORM>(D, geo, gamma, P.pts + 3 * q0, P.w + q0, FORM == CQ_FORM_NITSCHE ? P.normals + 3 * q0 : nullptr, (int)(q1 - q0), t, lat,
+                          valid);
 
     // ---- sink: lane holds D[ti][tj] at row 8*ti + g, cols 8*tj + 2*t + {0,1} -------------------
     const int bs = P.bs;

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <unordered_map>
 
 #include "../../include/cq_b200.h"
 #include "cq_kernels.cuh"
@@ -12,7 +13,7 @@ struct cq_ctx {
   int device = 0;
   int num_sms = 0;
   int variant = 0;
-  int* err_flag = nullptr;  // device
+  int* err_flag = nullptr;  // device: [0] sparsity violation seen by a kernel, [1] scratch word of the setup kernels
   unsigned int* work_counter = nullptr;  // device: dynamic stage counter of the staged kernels
   int max_smem_optin = 0;
   std::atomic<int64_t> launches{0};
@@ -33,12 +34,25 @@ struct cq_ctx {
   int fused_zero = 0;   // cq_ctx_set_fused_zero
   void* zero_buf = nullptr;
   size_t zero_waves = 0;
+  // multi-GPU (cq_comm.cu): NCCL communicator (resolved at run time), receive buffer, neighbour fence through peer memory
+  void* nccl_comm = nullptr;
+  int comm_rank = -1, comm_size = 0;
+  void* recv_buf = nullptr;
+  size_t recv_bytes = 0;
+  unsigned int* fence_flags = nullptr;  // device [2]: [0] written by the down neighbour, [1] by the up neighbour
+  unsigned int* fence_down = nullptr;   // mapped: the down neighbour's word [1]
+  unsigned int* fence_up = nullptr;     // mapped: the up neighbour's word [0]
+  unsigned int fence_epoch = 0;
+  // dynamic shared memory opt-in already granted on this device, per kernel (cq_launch.cuh:ensure_smem_optin)
+  std::unordered_map<const void*, size_t> smem_optin;
 };
 
 namespace cq {
 
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+
+void comm_release(cq_ctx* ctx);  // cq_comm.cu: frees the communicator, the receive buffer and the fence words
 
 // launchers implemented in cq_launch_*.cu; return cq_status
 int launch_matrix(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStream_t s);
@@ -48,7 +62,7 @@ int launch_scalar(cq_ctx* ctx, const cq_form_desc& f, const KParams& P, cudaStre
 // grid size for a grid-strided kernel: enough blocks for the work, at most a full wave
 template <auto Kernel>
 int grid_for(cq_ctx* ctx, int threads, int64_t work_per_block_unit, int64_t units, size_t smem = 0) {
-  static thread_local int blocks_per_sm = 0;  // one per kernel instantiation
+  static thread_local int blocks_per_sm = 0;  // one per kernel instantiation (an occupancy, the same on every B200)
   if (blocks_per_sm == 0) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, Kernel, threads, smem) != cudaSuccess || blocks_per_sm < 1)
       blocks_per_sm = 1;

@@ -37,7 +37,7 @@ struct KParams {
   int64_t num_points;                    // length of pts / w (bulk-copy tail handling)
   int stage_points;                      // points capacity of one smem stage
   int mesh_flags;                        // cq_mesh.flags
-  int dbg;                               // profiling experiments only (CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
+  int dbg;                               // profiling builds only (-DCQ_PROFILING, CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)
   int elem_out;    // 1: write un-scattered element tensors to out[k, :]
   // fused A.zeroEntries() (cq_assemble_matrix_zero, cq_zero.cuh): the kernel itself zeroes `values` just ahead of
@@ -72,6 +72,13 @@ CQ_DEVINL void transpose_reduce_step(double* acc, const int r) {
 }
 
 CQ_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// work-skipping experiments exist in profiling builds only; in the product CQ_DBG(P) is the constant 0
+#ifdef CQ_PROFILING
+#define CQ_DBG(P) ((P).dbg)
+#else
+#define CQ_DBG(P) 0
+#endif
 
 // position of (row, col) in a sorted-column CSR, -1 if absent (MatSetValuesLocal's row search)
 CQ_DEVINL int64_t csr_find(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int64_t row,

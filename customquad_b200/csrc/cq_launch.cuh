@@ -10,6 +10,28 @@ namespace cq {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Tuning / experiment switches read from the environment exist in profiling builds only (-DCQ_PROFILING,
+// profiles/build_variant*.sh): the shipped library has compile-time constants, so no environment variable can change
+// which code runs or skip work.
+#ifdef CQ_PROFILING
+static inline int tune_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+static inline double tune_f64(const char* name, double dflt) { const char* v = getenv(name); return v ? atof(v) : dflt; }
+#define CQ_TUNE_INT(name, dflt) tune_int(name, dflt)
+#define CQ_TUNE_F64(name, dflt) tune_f64(name, dflt)
+#else
+#define CQ_TUNE_INT(name, dflt) (dflt)
+#define CQ_TUNE_F64(name, dflt) (dflt)
+#endif
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and per kernel: remembered in the ctx (one per device)
+static int ensure_smem_optin(cq_ctx* ctx, const void* kernel, size_t smem) {
+  size_t& have = ctx->smem_optin[kernel];
+  if (smem <= have) return CQ_OK;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
+  have = smem;
+  return CQ_OK;
+}
+
 // ---- fused zeroEntries (cq_zero.cuh) ----------------------------------------------------------------
 // Sets P.zero_hi / zero_done / zero_ahead for a launch of `grid` CTAs (stream-ordered).  The caller has checked that
 // the kernel supports it; on return P.zero_req is cleared.
@@ -32,7 +54,7 @@ static int prepare_fused_zero(cq_ctx* ctx, KParams& P, const int n, const int gr
   wave_scan_kernel<><<<1, 1024, 0, s>>>(raw, waves);
   ctx->launches += 2;
   if (int rc = check_cuda(cudaGetLastError(), "fused-zero setup kernels")) return rc;
-  static const int ahead = getenv("CQ_ZERO_AHEAD") ? atoi(getenv("CQ_ZERO_AHEAD")) : 6;
+  const int ahead = CQ_TUNE_INT("CQ_ZERO_AHEAD", 6);
   P.zero_hi = reinterpret_cast<const long long*>(raw);
   P.zero_done = done;
   P.zero_ahead = ahead < 4 ? 4 : ahead;  // at least the batch of the zeroing warp (no deadlock: cq_staged_kernel.cuh)
@@ -80,20 +102,15 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
   if (budget / NPW <= fixed + 64 * per_point) { set_error("staged kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
   const int64_t pb_max = (int64_t)((budget / NPW - fixed) / per_point) & ~(int64_t)1;
-  static const double factor = getenv("CQ_STAGE_FACTOR") ? atof(getenv("CQ_STAGE_FACTOR")) : 1.25;  // stage capacity / mean stage size
+  const double factor = CQ_TUNE_F64("CQ_STAGE_FACTOR", 1.25);  // stage capacity / mean stage size
   int64_t pb = (int64_t)((P.num_points / (P.num_entries > 0 ? P.num_entries : 1) + 1) * CB * factor) + 64;
   pb = (pb + 1) & ~(int64_t)1;
   if (pb > pb_max) pb = pb_max;
   if (pb < 64) pb = 64;
   P.stage_points = (int)pb;
-  static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
-  P.dbg = dbg;
+  P.dbg = CQ_TUNE_INT("CQ_DEBUG", 0);
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
-  static thread_local size_t configured = 0;  // per kernel instantiation
-  if (smem > configured) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
-    configured = smem;
-  }
+  if (int rc = ensure_smem_optin(ctx, (const void*)kernel, smem)) return rc;
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
   kernel<<<grid, (NPW + NCW) * 32, smem, s>>>(P);
@@ -117,7 +134,7 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
   if (budget / NPW <= fixed + 64 * per_point) { set_error("moment kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
   const int64_t pb_max = (int64_t)((budget / NPW - fixed) / per_point) & ~(int64_t)1;
-  static const double factor = getenv("CQ_STAGE_FACTOR") ? atof(getenv("CQ_STAGE_FACTOR")) : 1.25;
+  const double factor = CQ_TUNE_F64("CQ_STAGE_FACTOR", 1.25);
   int64_t pb = (int64_t)((P.num_points / (P.num_entries > 0 ? P.num_entries : 1) + 1) * CB * factor) + 64;
   pb = (pb + 1) & ~(int64_t)1;
   if (pb > pb_max) pb = pb_max;
@@ -130,14 +147,9 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
     if (pb > pb_max) { set_error("moment kernel: expansion tiles do not fit the stage"); return CQ_ERR_UNSUPPORTED; }
   }
   P.stage_points = (int)pb;
-  static const int dbg = getenv("CQ_DEBUG") ? atoi(getenv("CQ_DEBUG")) : 0;
-  P.dbg = dbg;
+  P.dbg = CQ_TUNE_INT("CQ_DEBUG", 0);
   const size_t smem = NPW * Lay::stage_bytes((int)pb);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)")) return rc;
-    configured = smem;
-  }
+  if (int rc = ensure_smem_optin(ctx, (const void*)kernel, smem)) return rc;
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
   if (P.zero_req) {
@@ -244,7 +256,7 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // three-role kernel for Q1 (measured 1.00 vs 1.06 ms on the bench workload); for Q2 both
         // organisations are bound by the L2 atomic rate of the 81 REDs per cell (2.56 vs 2.59 ms)
         // split = 2: row-owned expansion + transposed scatter (RowTile, cq_moment.cuh)
-        static const int split = getenv("CQ_MOMENT_SPLIT") ? atoi(getenv("CQ_MOMENT_SPLIT")) : 2;
+        const int split = CQ_TUNE_INT("CQ_MOMENT_SPLIT", 2);
         if (split == 2) {
           // fused zeroEntries (opt-in, cq_ctx_set_fused_zero): one more warp.  Q1: 4 + 8 + 2 + 1 warps still cost 16
           // warps' worth of registers; Q2: 4 + 6 + 6 = 16 warps at 128 registers, so the zeroing warp takes the place

@@ -761,7 +761,7 @@ template <class T, int G, int CB>
 CQ_DEVINL void moment_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, const bool active, const int r) {
   double mu[2 * T::DEG + 1][2 * T::DEG + 1];
   moment_accumulate<T, G, CB>(M, e, active, r, mu);
-  if (!active || P.dbg == 2) return;
+  if (!active || CQ_DBG(P) == 2) return;
   moment_expand<T, G, CB, 0, 1>(P, M, e, r, mu);
 }
 

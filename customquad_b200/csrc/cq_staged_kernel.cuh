@@ -356,7 +356,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
         if (nent < 0) {
           ended |= 1u << s;
         } else {
-          for (; P.dbg != 1;) {
+          for (; CQ_DBG(P) != 1;) {
             int e0 = 0;
             if (lane == 0) e0 = atomicAdd(&M.next, CPW);
             e0 = __shfl_sync(0xffffffffu, e0, 0);
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
             if (e0 >= nent) break;
             const bool active = e0 + grp < nent;
             const int e = active ? M.order[e0 + grp] : 0;
-            moment_accumulate_store<T, G, CB>(M, e, active, P.dbg != 1, r);
+            moment_accumulate_store<T, G, CB>(M, e, active, CQ_DBG(P) != 1, r);
           }
         }
         __syncwarp();
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
             // this warp's tile lives in the stage's point buffer (dead after the moment phase)
             using RT = RowTile<T::DIM, T::DEG>;
             double* tile = reinterpret_cast<double*>(smem_raw + (size_t)s * stage_bytes + Lay::meta_bytes + (size_t)role * RT::bytes(CB));
-            if (P.dbg != 2) {
+            if (CQ_DBG(P) != 2) {
               static_for<0, T::DEG + 1>([&](auto RR) {
                 if (role == decltype(RR)::value) {
                   if (lane < nent) moment_expand_rows<T, CB, decltype(RR)::value>(M, lane, tile + lane * RT::STRIDE);
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
              zwait(wave);
              zload(wave + NXS);
            }
-           if (lane < nent && P.dbg != 2) {
+           if (lane < nent && CQ_DBG(P) != 2) {
             double mu[Pn][Pn];
 #pragma unroll
             for (int p = 0; p < Pn; ++p)

@@ -41,6 +41,7 @@ class Slab:
 def partition_layers(n_layers: int, world: int, weights=None) -> np.ndarray:
     """Slab boundaries [world+1] along the slab axis.  With `weights` (work per layer, e.g. the sum
     of nq*n^2 over the layer's cells) the split balances work, not cell count."""
+    assert n_layers >= world, f"{world} ranks need at least {world} cell layers along the slab axis (got {n_layers})"
     if weights is None:
         return np.array([n_layers * r // world for r in range(world + 1)], dtype=np.int64)
     w = np.asarray(weights, dtype=np.float64)
@@ -64,6 +65,7 @@ def make_slab(points, n, rank: int, world: int, bounds=None) -> Slab:
     axis = 0 if tdim == 2 else 2  # slowest cell axis of the mesh generators
     b = partition_layers(n[axis], world) if bounds is None else np.asarray(bounds)
     first, last = int(b[rank]), int(b[rank + 1])
+    assert last > first, f"rank {rank} owns no cell layer (bounds {list(map(int, b))})"
     ghost = 1 if rank > 0 else 0
     lo = first - ghost
     h = (p[1, axis] - p[0, axis]) / n[axis]
@@ -120,9 +122,10 @@ class SlabExchange:
             below = cols < r1  # columns on lines <= interface line  (col id = line*line_size + ...)
             cnt = np.add.reduceat(below.astype(np.int64), (ip[:-1] - ip[0])) if len(cols) else np.zeros(self.line, np.int64)
             # prefix property: the `cnt[r]` columns below the interface are the first entries of the row
+            # (checked on every interface row: one-time setup)
             starts = ip[:-1] - ip[0]
-            for r in (0, self.line // 2, self.line - 1):
-                assert below[starts[r] : starts[r] + cnt[r]].all()
+            pos_in_row = np.arange(len(cols)) - np.repeat(starts, np.diff(ip))
+            assert np.array_equal(below, pos_in_row < np.repeat(cnt, np.diff(ip))), "sender rows are not prefixes of the owner's rows"
             self.recv_indptr_host = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
         if self.has_up:
             ip = _to_numpy(indptr[self.send_row0 : self.nrows + 1])
@@ -135,6 +138,22 @@ class SlabExchange:
 
         if getattr(self, "peer", False) and not force_nccl:  # the kernels already scattered into the owner's memory
             self.fence(values.device)
+            return
+        if self._acc_rows is None and values.is_cuda and ensure_comm(values.device, self.group):
+            # the whole exchange inside the library: grouped ncclSend / ncclRecv + accumulate kernel (cq_exchange_offrank)
+            import ctypes as C
+
+            from . import _lib
+
+            if self.has_down and (self.recv_indptr is None or self.recv_indptr.device != values.device):
+                self.recv_indptr = torch.from_numpy(self.recv_indptr_host).to(values.device)
+            A = _lib.CsrDesc(int(self.indptr.shape[0] - 1), int(values.shape[0]), C.c_void_p(self.indptr.data_ptr()), None, C.c_void_p(values.data_ptr()))
+            _lib.check(_lib.load().cq_exchange_offrank(
+                _lib.ctx(values.device.index), C.byref(A),
+                self.slab.rank + 1 if self.has_up else -1, self.send_lo if self.has_up else 0, self.send_hi if self.has_up else 0,
+                self.slab.rank - 1 if self.has_down else -1, self.recv_row0, self.line if self.has_down else 0,
+                C.c_void_p(self.recv_indptr.data_ptr()) if self.has_down else None, int(self.recv_indptr_host[-1]) if self.has_down else 0,
+                C.c_void_p(torch.cuda.current_stream().cuda_stream)))  # fmt: skip
             return
 
         ops, recv = [], None
@@ -195,6 +214,7 @@ class SlabExchange:
                 _lib.check(L.cq_ipc_open(ctx, hbuf, off, C.byref(ptr), C.byref(base)))
                 delta = ptr.value - A.data.data_ptr()
                 assert delta % 8 == 0
+                _open_mappings.append((dev.index, base.value))
                 # sender row j of the top line is a prefix of the owner's row: same position inside the row
                 table = rows + delta // 8
                 self._peer_base = base
@@ -208,6 +228,11 @@ class SlabExchange:
             A.peer_row0, A.peer_rowstart = None, None
             return False
         self.peer = True
+        # the owner side: a neighbour's kernels add into this matrix at any time between two fences, so zeroing it
+        # needs the zero -> fence -> assemble -> fence protocol (assemble_matrix(..., zero=True) follows it)
+        A.peer_target = self.has_down
+        A.peer_exchange = self
+        setup_peer_fence(dev, self.group)
         return True
 
     def fence(self, device):
@@ -216,6 +241,14 @@ class SlabExchange:
         import torch
         import torch.distributed as dist
 
+        if _peer_fence_ready.get(device.index):
+            # flag words in the neighbours' memory (cq_peer_fence): one single-thread kernel, no NCCL in the step
+            import ctypes as C
+
+            from . import _lib
+
+            _lib.check(_lib.load().cq_peer_fence(_lib.ctx(device.index), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            return
         if not hasattr(self, "_fence_buf") or self._fence_buf.device != device:
             self._fence_buf = torch.zeros(1, dtype=torch.float32, device=device)
         dist.all_reduce(self._fence_buf, group=self.group)
@@ -225,6 +258,17 @@ class SlabExchange:
         import torch
         import torch.distributed as dist
 
+        if self._axpy is None and b.is_cuda and ensure_comm(b.device, self.group):
+            import ctypes as C
+
+            from . import _lib
+
+            _lib.check(_lib.load().cq_exchange_offrank_vector(
+                _lib.ctx(b.device.index), C.c_void_p(b.data_ptr()),
+                self.slab.rank + 1 if self.has_up else -1, self.send_row0, self.nrows,
+                self.slab.rank - 1 if self.has_down else -1, self.recv_row0, self.line if self.has_down else 0,
+                C.c_void_p(torch.cuda.current_stream().cuda_stream)))  # fmt: skip
+            return
         ops, recv = [], None
         if self.has_up:
             ops.append(dist.P2POp(dist.isend, b[self.send_row0 : self.nrows], self.slab.rank + 1, self.group))
@@ -244,8 +288,111 @@ class SlabExchange:
         import torch.distributed as dist
 
         t = torch.tensor([m], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if t.is_cuda and ensure_comm(t.device, group):
+            import ctypes as C
+
+            from . import _lib
+
+            _lib.check(_lib.load().cq_allreduce_sum(_lib.ctx(t.device.index), C.c_void_p(t.data_ptr()), 1, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return float(t.item())
+
+
+# ---- process-wide state of the library-side communication (one cq_ctx per device per process) -------------------
+_comm_ready: dict = {}        # device index -> bool: cq_comm_init done (NCCL communicator inside the cq_ctx)
+_peer_fence_ready: dict = {}  # device index -> bool: cq_peer_fence_setup done
+_open_mappings: list = []     # (device index, mapped base) of every cq_ipc_open, closed by close_peer_mappings()
+
+
+def ensure_comm(device, group=None) -> bool:
+    """Collective, once per process: create the NCCL communicator inside this device's cq_ctx (cq_comm_unique_id on
+    rank 0, broadcast through torch.distributed, cq_comm_init).  CQ_DIST_TORCH=1 keeps the torch.distributed
+    send/recv path instead.  Returns whether the library-side exchange (cq_exchange_offrank) can be used."""
+    import ctypes as C
+    import os
+
+    import torch.distributed as dist
+
+    from . import _lib
+
+    if device.index in _comm_ready:
+        return _comm_ready[device.index]
+    ok = os.environ.get("CQ_DIST_TORCH", "0") != "1"
+    ident = [None]
+    if ok and dist.get_rank(group) == 0:
+        buf = (C.c_ubyte * 128)()
+        ok = _lib.load().cq_comm_unique_id(buf) == 0
+        ident = [bytes(buf) if ok else None]
+    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    mine = False
+    if ident[0] is not None:
+        buf = (C.c_ubyte * 128).from_buffer_copy(ident[0])
+        mine = _lib.load().cq_comm_init(_lib.ctx(device.index), dist.get_world_size(group), dist.get_rank(group), buf) == 0
+    flags = [None] * dist.get_world_size(group)
+    dist.all_gather_object(flags, mine, group=group)
+    _comm_ready[device.index] = all(flags)
+    return _comm_ready[device.index]
+
+
+def setup_peer_fence(device, group=None) -> bool:
+    """Collective, once per process: every rank maps the fence words of its two slab neighbours (CUDA IPC) so that
+    SlabExchange.fence is one small kernel (cq_peer_fence) instead of an NCCL all-reduce.  CQ_PEER_FENCE=0 keeps NCCL."""
+    import ctypes as C
+    import os
+
+    import torch.distributed as dist
+
+    from . import _lib
+
+    if device.index in _peer_fence_ready:
+        return _peer_fence_ready[device.index]
+    L = _lib.load()
+    ctx = _lib.ctx(device.index)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = None
+    if os.environ.get("CQ_PEER_FENCE", "1") != "0":
+        try:
+            p = L.cq_peer_flags(ctx)
+            handle, off = (C.c_ubyte * 64)(), C.c_int64(0)
+            _lib.check(L.cq_ipc_export(ctx, C.c_void_p(p), handle, C.byref(off)))
+            mine = (bytes(handle), int(off.value))
+        except Exception:  # noqa: BLE001 -- any failure => everybody keeps the NCCL fence
+            mine = None
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    ok = all(g is not None for g in gathered)
+    if ok:
+        try:
+            ptrs = [None, None]
+            for k, nb in enumerate((rank - 1, rank + 1)):
+                if 0 <= nb < world:
+                    handle, off = gathered[nb]
+                    ptr, base = C.c_void_p(), C.c_void_p()
+                    _lib.check(L.cq_ipc_open(ctx, (C.c_ubyte * 64).from_buffer_copy(handle), off, C.byref(ptr), C.byref(base)))
+                    _open_mappings.append((device.index, base.value))
+                    # word [1] of the down neighbour is written by its up neighbour (this rank); word [0] of the up neighbour by its down neighbour
+                    ptrs[k] = C.c_void_p(ptr.value + (4 if k == 0 else 0))
+            _lib.check(L.cq_peer_fence_setup(ctx, ptrs[0], ptrs[1]))
+        except Exception:  # noqa: BLE001
+            ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)
+    _peer_fence_ready[device.index] = all(flags)
+    dist.barrier(group=group)
+    return _peer_fence_ready[device.index]
+
+
+def close_peer_mappings() -> None:
+    """Unmap every neighbour allocation this process opened (cq_ipc_close); call once at teardown, after a barrier."""
+    import ctypes as C
+
+    from . import _lib
+
+    while _open_mappings:
+        dev, base = _open_mappings.pop()
+        _lib.load().cq_ipc_close(_lib.ctx(dev), C.c_void_p(base))
+    _peer_fence_ready.clear()
 
 
 def _to_numpy(t):

@@ -126,7 +126,7 @@ def form(obj, kind: str, f=None, betaN: float | None = None):
     W = function_space(V)
     if kind not in _KINDS:
         raise ValueError(f"unknown integrand {kind!r}; one of {sorted(_KINDS)}")
-    if f is not None and not isinstance(f, (_forms.Analytic, Function)):
+    if f is not None and not isinstance(f, (_forms.Analytic, Function)) and not np.isscalar(f):  # numbers pass through (forms._data)
         f = function(f, W)
     return _KINDS[kind](W, f=f, betaN=betaN)
 

@@ -128,6 +128,11 @@ class Form:
 
 def _data(V_or_mesh, f, bs):
     if isinstance(f, Function):
+        # the kernels index the packed coefficient with the FORM's degree and block size (cq_space.coeffs [cells, n*bs])
+        if isinstance(V_or_mesh, FunctionSpace):
+            W = f.function_space
+            assert W is V_or_mesh or (W.degree == V_or_mesh.degree and W.bs == V_or_mesh.bs and W.mesh is V_or_mesh.mesh), \
+                "the coefficient must live in the form's space (same mesh, degree and block size)"
         return f, None
     if isinstance(f, Analytic):
         assert f.ncomp() == bs, f"function has {f.ncomp()} components, space has bs={bs}"

@@ -22,6 +22,8 @@ class CSRMatrix:
         # into the owner rank's values over NVLink; peer_rowstart is the device slot table (cq_csr)
         self.peer_row0 = None
         self.peer_rowstart = None
+        self.peer_target = False    # a neighbour's kernels add into this matrix (cq_csr.flags & CQ_CSR_PEER_TARGET)
+        self.peer_exchange = None   # the SlabExchange whose fence orders the zeroing against the neighbours
 
     @property
     def size(self):

@@ -25,6 +25,10 @@
  *                          the scatter (the analogue of utils.print_for_header, utils.py:185-225)
  *   cq_csr_accumulate_rows <- the receive side of PETSc MatAssemblyBegin/End after
  *                          A.assemble() (README.md:95, demo/poisson.py:194)
+ *   cq_exchange_offrank <- that whole stash exchange (send the rows a neighbour owns, receive and
+ *                          add the neighbour's contributions to the rows this rank owns), NCCL send/recv
+ *   cq_assemble_matrices_host <- several assemble_matrix calls on ONE qr tuple (demo/poisson.py:193,209
+ *                          reuse qr_bulk for a matrix and a vector): the rule crosses PCIe once
  */
 #ifndef CQ_B200_H
 #define CQ_B200_H
@@ -35,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CQ_B200_ABI_VERSION 3
+#define CQ_B200_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------ */
 typedef enum cq_status {
@@ -164,7 +168,14 @@ typedef struct cq_csr {
    * peer_row0 = num_rows and peer_rowstart = NULL when unused. */
   int64_t peer_row0;
   const int64_t* peer_rowstart;
+  /* CQ_CSR_PEER_TARGET: a neighbour rank's kernels add into `values` over NVLink (this rank is the owner side of
+   * a peer scatter).  Zeroing such a matrix has to be ordered against the neighbour by the caller (zero, fence,
+   * assemble, fence): cq_assemble_matrix_zero / the *_host entry points refuse it with CQ_ERR_UNSUPPORTED. */
+  int32_t flags;
+  int32_t pad_;
 } cq_csr;
+
+#define CQ_CSR_PEER_TARGET 1
 
 typedef struct cq_ctx cq_ctx;
 
@@ -183,7 +194,7 @@ int64_t cq_ctx_launch_count(const cq_ctx* ctx);
  * kernel only (error when not applicable), 3 = like 0 but never the moment kernels. */
 int cq_ctx_set_variant(cq_ctx* ctx, int variant);
 /* 1: cq_assemble_matrix_zero zeroes inside the persistent moment kernels (quadrilaterals; cooperative
- * launch), 0 (default, or the CQ_ZERO_FUSED environment variable at ctx creation): memset first. */
+ * launch), 0 (default): memset first.  Same result either way. */
 int cq_ctx_set_fused_zero(cq_ctx* ctx, int on);
 
 /* ---- the hot path (device pointers) ---------------------------------------------------- */
@@ -318,6 +329,57 @@ int cq_assemble_vector_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh
 int cq_assemble_scalar_host(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
                             const cq_space* space, const cq_quadrature* qr_host, double* m_host,
                             void* stream);
+
+/* Several bilinear forms over the SAME qr tuple (the reference's demo integrates its bulk rule into a matrix
+ * and a vector, demo/poisson.py:193,209; bench.py assembles stiffness and mass of two spaces): the rule is
+ * uploaded once, in chunks; every chunk runs the kernels of all jobs; the finished rows of every matrix go
+ * back to the host while later chunks are still coming in.  Each A is zeroed first (assemble_matrix.py:20).
+ * Equivalent to njobs calls of cq_assemble_matrix_host, minus (njobs - 1) uploads of the rule. */
+typedef struct cq_matrix_job {
+  const cq_form_desc* form;
+  const cq_space* space;
+  const cq_csr* A;
+  double* values_host;  /* [A->nnz] host (ideally pinned) or NULL: keep the result on the device */
+} cq_matrix_job;
+int cq_assemble_matrices_host(cq_ctx* ctx, int njobs, const cq_matrix_job* jobs, const cq_mesh* mesh,
+                              const cq_quadrature* qr_host, void* stream);
+
+/* ---- multi-GPU exchange inside the library (one process per GPU) ------------------------------------
+ * The NCCL communicator lives in the ctx, so that a non-Python host can run the cell-partitioned assembly
+ * (cq_exchange_offrank).  libnccl.so.2 is resolved at run time (the copy already loaded into the
+ * process, e.g. torch's, else the system one): the library does not link against it.
+ *   rank 0: cq_comm_unique_id(id); broadcast id by any means; every rank: cq_comm_init(ctx, n, rank, id). */
+#define CQ_COMM_ID_BYTES 128
+int cq_comm_unique_id(unsigned char id[CQ_COMM_ID_BYTES]);
+int cq_comm_init(cq_ctx* ctx, int nranks, int rank, const unsigned char id[CQ_COMM_ID_BYTES]);
+int cq_comm_destroy(cq_ctx* ctx);
+/* The stash exchange of A.assemble() for a slab partition (customquad_b200/dist.py): this rank's value slots
+ * [send_lo, send_hi) -- its contributions to rows owned by rank `up` -- are sent to `up` (up < 0: nothing to
+ * send); `recv_count` values arrive from rank `down` (down < 0: nothing) and are added to the rows
+ * [recv_row0, recv_row0 + recv_nrows): values[indptr[recv_row0 + r] + i] += recv[recv_indptr[r] + i]
+ * (a sender row is a prefix of the owner's row; recv_indptr [recv_nrows + 1] int64 on the device,
+ * recv_indptr[recv_nrows] == recv_count).  One grouped ncclSend / ncclRecv plus cq_csr_accumulate_rows,
+ * all on `stream`. */
+int cq_exchange_offrank(cq_ctx* ctx, const cq_csr* A, int up, int64_t send_lo, int64_t send_hi, int down,
+                        int64_t recv_row0, int64_t recv_nrows, const int64_t* recv_indptr, int64_t recv_count,
+                        void* stream);
+/* The same for a vector: b[send_lo .. send_hi) goes up, recv_count values from `down` are added at b[recv_lo ..). */
+int cq_exchange_offrank_vector(cq_ctx* ctx, double* b, int up, int64_t send_lo, int64_t send_hi, int down,
+                               int64_t recv_lo, int64_t recv_count, void* stream);
+/* In-place sum of n doubles (device) over all ranks: assemble_scalar's missing MPI reduction (assemble_scalar.py:34). */
+int cq_allreduce_sum(cq_ctx* ctx, double* x, int64_t n, void* stream);
+
+/* ---- neighbour fence through peer memory (no NCCL in the step) ------------------------------------------
+ * The fused peer scatter needs two stream-ordered barriers with the two slab neighbours per matrix (after the
+ * zeroing, after the kernel).  Each ctx owns two flag words; the neighbours map them (cq_ipc_export of
+ * cq_peer_flags(ctx), cq_ipc_open on their side) and hand the mapped addresses to cq_peer_fence_setup:
+ * flag_in_down / flag_in_up = the word of the DOWN / UP neighbour that this rank writes (NULL: no such
+ * neighbour).  cq_peer_fence enqueues one single-thread kernel on `stream`: release-store the next epoch into
+ * the neighbours' words, then acquire-spin on the own words until both neighbours have reached it.  Every rank
+ * has to call it the same number of times. */
+void* cq_peer_flags(cq_ctx* ctx);  /* device address of this ctx's two flag words: [0] written by down, [1] by up */
+int cq_peer_fence_setup(cq_ctx* ctx, void* flag_in_down, void* flag_in_up);
+int cq_peer_fence(cq_ctx* ctx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,6 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../customquad_b200"
 mkdir -p ../build/variants
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -diag-suppress 177 -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c csrc/cq_launch_matrix.cu -o ../build/variants/lm_$name.o
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../build/variants/libcq_$name.so csrc/cq_api.o ../build/variants/lm_$name.o csrc/cq_launch_vector.o csrc/cq_launch_scalar.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -diag-suppress 177 -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DCQ_PROFILING "$@" -c csrc/cq_launch_matrix.cu -o ../build/variants/lm_$name.o
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../build/variants/libcq_$name.so csrc/cq_api.o csrc/cq_comm.o ../build/variants/lm_$name.o csrc/cq_launch_vector.o csrc/cq_launch_scalar.o -lcudart -ldl
 echo build/variants/libcq_$name.so

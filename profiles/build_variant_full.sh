@@ -5,10 +5,10 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../customquad_b200"
 mkdir -p ../build/variants
-F="-gencode arch=compute_100a,code=sm_100a -lineinfo -diag-suppress 177 -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
+F="-gencode arch=compute_100a,code=sm_100a -lineinfo -diag-suppress 177 -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DCQ_PROFILING"
 for tu in matrix vector scalar; do
   nvcc $F "$@" -c csrc/cq_launch_$tu.cu -o ../build/variants/l${tu}_$name.o &
 done
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../build/variants/libcq_$name.so csrc/cq_api.o ../build/variants/lmatrix_$name.o ../build/variants/lvector_$name.o ../build/variants/lscalar_$name.o -lcudart
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../build/variants/libcq_$name.so csrc/cq_api.o csrc/cq_comm.o ../build/variants/lmatrix_$name.o ../build/variants/lvector_$name.o ../build/variants/lscalar_$name.o -lcudart -ldl
 echo build/variants/libcq_$name.so

@@ -17,7 +17,8 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ("cq_assemble_matrix", "cq_assemble_vector", "cq_assemble_scalar", "cq_ctx_create", "cq_ctx_destroy", "cq_last_error",
-              "cq_assemble_matrix_host", "cq_csr_accumulate_rows", "cq_tabulate", "cq_element_tensors"):  # fmt: skip
+              "cq_assemble_matrix_host", "cq_csr_accumulate_rows", "cq_tabulate", "cq_element_tensors", "cq_exchange_offrank",
+              "cq_assemble_matrices_host", "cq_comm_init", "cq_peer_fence"):  # fmt: skip
         assert s in syms
 
 
@@ -32,8 +33,9 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/cq_b200.h but not exported"
     L.cq_abi_version.restype = ctypes.c_int
-    # 2: cq_csr.peer_row0 / peer_rowstart, cq_ipc_*; 3: cq_assemble_matrix_zero, cq_ctx_set_fused_zero, cq_circle_*, cq_sphere_*
-    assert L.cq_abi_version() == 3
+    # 2: cq_csr.peer_row0 / peer_rowstart, cq_ipc_*; 3: cq_assemble_matrix_zero, cq_ctx_set_fused_zero, cq_circle_*, cq_sphere_*;
+    # 4: cq_csr.flags, cq_assemble_matrices_host, cq_comm_*, cq_exchange_offrank*, cq_allreduce_sum, cq_peer_fence*
+    assert L.cq_abi_version() == 4
     assert set(_lib._SIGNATURES) == set(declared_symbols())
 
 
