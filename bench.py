@@ -121,7 +121,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
-    from customquad_b200.sparsity import build_pattern
+    from oracle.oracle import build_pattern  # the oracle's own builder (oracle/cq_oracle.c)
 
     oracle.build()
     threads = oracle.max_threads()
@@ -166,7 +166,7 @@ def workload_config(n_gpus):
 def cpu_baseline_sample():
     """Oracle (port) on the GPU box's host cores: a bounded sample of the same workload."""
     from oracle import oracle
-    from customquad_b200.sparsity import build_pattern
+    from oracle.oracle import build_pattern  # the oracle's own builder (oracle/cq_oracle.c)
 
     threads = oracle.max_threads()
     cols = 512  # 512 x 2048 = 1,048,576 cells (a quarter of the workload), all 4 forms once

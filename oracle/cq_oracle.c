@@ -482,6 +482,79 @@ int cq_oracle_tabulate(int cell_type, int degree, int basix_derivative, int64_t 
   return nbf;
 }
 
+/* ---------------------------------------------------------------------------------------
+ * dolfinx.cpp.fem.petsc.create_matrix(form) (assemble_matrix.py:19): the AIJ sparsity pattern of the form's cell
+ * integral.  Restated the way dolfinx's SparsityPattern / PETSc preallocation build it: for every cell of the
+ * integration domain insert dofs[c] x dofs[c]; a row is a sorted array of distinct columns grown by insertion.
+ * Blocked spaces: row r*bs + a holds the columns c*bs + b, b < bs, of every scalar coupling (r, c)
+ * (utils.py:59-62 interleaving).  Own implementation: independent of customquad_b200/sparsity.py,
+ * so that "bit-exact sparsity" compares two builders.
+ * cells == NULL: all cells (dx_cut without subdomain id, demo/poisson.py:180,189); else the listed cells.
+ * --------------------------------------------------------------------------------------- */
+typedef struct oracle_pattern {
+  int64_t num_dofs;
+  int64_t* start;   /* [num_dofs + 1] capacity offsets */
+  int32_t* len;     /* [num_dofs] columns currently in the row */
+  int32_t* cols;    /* [start[num_dofs]] */
+} oracle_pattern;
+
+void cq_oracle_pattern_free(oracle_pattern* p) {
+  if (!p) return;
+  free(p->start); free(p->len); free(p->cols); free(p);
+}
+
+oracle_pattern* cq_oracle_pattern_build(const int32_t* dofmap, int64_t num_cells, int n, int64_t num_dofs, const int32_t* cells, int64_t ncells_listed) {
+  oracle_pattern* p = (oracle_pattern*)calloc(1, sizeof *p);
+  p->num_dofs = num_dofs;
+  p->start = (int64_t*)calloc((size_t)num_dofs + 1, sizeof(int64_t));
+  p->len = (int32_t*)calloc((size_t)num_dofs > 0 ? (size_t)num_dofs : 1, sizeof(int32_t));
+  const int64_t nc = cells ? ncells_listed : num_cells;
+  /* preallocation: a row gets room for n columns per cell that touches it (an upper bound) */
+  for (int64_t k = 0; k < nc; ++k) {
+    const int32_t* d = dofmap + (size_t)(cells ? cells[k] : k) * n;
+    for (int i = 0; i < n; ++i) p->start[d[i] + 1] += n;
+  }
+  for (int64_t r = 0; r < num_dofs; ++r) p->start[r + 1] += p->start[r];
+  p->cols = (int32_t*)malloc(sizeof(int32_t) * (size_t)(p->start[num_dofs] > 0 ? p->start[num_dofs] : 1));
+  for (int64_t k = 0; k < nc; ++k) {
+    const int32_t* d = dofmap + (size_t)(cells ? cells[k] : k) * n;
+    for (int i = 0; i < n; ++i) {
+      int32_t* row = p->cols + p->start[d[i]];
+      int32_t m = p->len[d[i]];
+      for (int j = 0; j < n; ++j) {
+        const int32_t c = d[j];
+        int32_t lo = 0, hi = m;
+        while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (row[mid] < c) lo = mid + 1; else hi = mid; }
+        if (lo < m && row[lo] == c) continue;
+        memmove(row + lo + 1, row + lo, sizeof(int32_t) * (size_t)(m - lo));
+        row[lo] = c;
+        ++m;
+      }
+      p->len[d[i]] = m;
+    }
+  }
+  return p;
+}
+
+int64_t cq_oracle_pattern_nnz(const oracle_pattern* p, int bs) {
+  int64_t s = 0;
+  for (int64_t r = 0; r < p->num_dofs; ++r) s += p->len[r];
+  return s * bs * bs;
+}
+
+/* indptr [num_dofs*bs + 1] int64, indices [nnz] int32 */
+void cq_oracle_pattern_export(const oracle_pattern* p, int bs, int64_t* indptr, int32_t* indices) {
+  int64_t at = 0;
+  indptr[0] = 0;
+  for (int64_t r = 0; r < p->num_dofs; ++r)
+    for (int a = 0; a < bs; ++a) {
+      const int32_t* row = p->cols + p->start[r];
+      for (int32_t k = 0; k < p->len[r]; ++k)
+        for (int b = 0; b < bs; ++b) indices[at++] = row[k] * bs + b;
+      indptr[r * bs + a + 1] = at;
+    }
+}
+
 int cq_oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -66,6 +66,14 @@ def lib():
         L.cq_oracle_max_threads.argtypes = []
         L.cq_oracle_tabulate.restype = C.c_int
         L.cq_oracle_tabulate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+        L.cq_oracle_pattern_build.restype = C.c_void_p
+        L.cq_oracle_pattern_build.argtypes = [P, C.c_int64, C.c_int, C.c_int64, P, C.c_int64]
+        L.cq_oracle_pattern_nnz.restype = C.c_int64
+        L.cq_oracle_pattern_nnz.argtypes = [P, C.c_int]
+        L.cq_oracle_pattern_export.restype = None
+        L.cq_oracle_pattern_export.argtypes = [P, C.c_int, P, P]
+        L.cq_oracle_pattern_free.restype = None
+        L.cq_oracle_pattern_free.argtypes = [P]
         if os.environ.get("CQ_ORACLE_BACKTRACE"):
             L.cq_oracle_install_segv_handler()
         _LIB = L
@@ -76,17 +84,78 @@ def max_threads() -> int:
     return int(lib().cq_oracle_max_threads())
 
 
+# ---- the oracle's own input normalisation and sparsity (independent of customquad_b200/quadrature.py, sparsity.py) ----
+class _Rule:
+    """One qr_data tuple as the C loop wants it: what ``for k, cell in enumerate(cells): ... qr_pts[k], qr_w[k], qr_n[k]``
+    (assemble_matrix.py:65-73,84-101) walks over, laid end to end."""
+
+    def __init__(self, cells, offsets, pts, w, n):
+        self.cells, self.offsets, self.pts, self.w, self.n = cells, offsets, pts, w, n
+        self.num_entries = int(cells.shape[0])
+
+
+def _rule(qr, gdim: int) -> _Rule:
+    if all(hasattr(qr, a) for a in ("cells", "offsets", "pts", "w", "n")):  # already flat arrays (data, no logic involved)
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        return _Rule(np.ascontiguousarray(qr.cells, dtype=np.int32), np.ascontiguousarray(qr.offsets, dtype=np.int64), f64(qr.pts), f64(qr.w), f64(qr.n))
+    assert len(qr) in (3, 4)  # assemble_matrix.py:65-69
+    cells = [int(c) for c in qr[0]]
+    qr_pts, qr_w = qr[1], qr[2]
+    qr_n = qr[3] if len(qr) == 4 else None
+    assert len(cells) == len(qr_pts) and len(cells) == len(qr_w)  # :70-73
+    if qr_n is not None:
+        assert len(cells) == len(qr_n)
+    offsets = np.zeros(len(cells) + 1, dtype=np.int64)
+    pts, w, n = [], [], []
+    for k in range(len(cells)):  # the reference's loop order (:84)
+        wk = np.asarray(qr_w[k], dtype=np.float64).reshape(-1)
+        pk = np.asarray(qr_pts[k], dtype=np.float64).reshape(-1)
+        assert pk.size == gdim * wk.size, "qr_pts[k] must hold gdim coordinates per weight"
+        offsets[k + 1] = offsets[k] + wk.size  # nq = len(qr_w[k]) (:87)
+        pts.append(pk)
+        w.append(wk)
+        if qr_n is not None:
+            nk = np.asarray(qr_n[k], dtype=np.float64).reshape(-1)
+            assert nk.size == pk.size
+            n.append(nk)
+    cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0)  # noqa: E731
+    return _Rule(np.asarray(cells, dtype=np.int32), offsets, cat(pts), cat(w), cat(n) if qr_n is not None else None)
+
+
+class Pattern:
+    def __init__(self, indptr, indices, num_rows):
+        self.indptr, self.indices, self.num_rows = indptr, indices, num_rows
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indptr[-1])
+
+
+def build_pattern(dofmap, num_dofs: int, bs: int = 1, cells=None) -> Pattern:
+    """dolfinx.cpp.fem.petsc.create_matrix(form) restated in oracle/cq_oracle.c (insertion-sorted rows)."""
+    L = lib()
+    d = np.ascontiguousarray(dofmap, dtype=np.int32)
+    c = None if cells is None else np.ascontiguousarray(cells, dtype=np.int32)
+    h = L.cq_oracle_pattern_build(_ptr(d), d.shape[0], d.shape[1], int(num_dofs), _ptr(c), 0 if c is None else c.shape[0])
+    try:
+        nnz = int(L.cq_oracle_pattern_nnz(h, int(bs)))
+        indptr = np.zeros(int(num_dofs) * bs + 1, dtype=np.int64)
+        indices = np.zeros(nnz, dtype=np.int32)
+        L.cq_oracle_pattern_export(h, int(bs), _ptr(indptr), _ptr(indices))
+    finally:
+        L.cq_oracle_pattern_free(h)
+    return Pattern(indptr, indices, int(num_dofs) * bs)
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
 def _prepare(form, qr, nthreads, faithful):
     """Host steps of the reference's assemble_* drivers (assemble_matrix.py:11-17)."""
-    from customquad_b200.quadrature import normalise_qr  # host-side data model only
-
     mesh = form.mesh
     gdim = mesh.geometry.dim
-    q = normalise_qr(qr, gdim)
+    q = _rule(qr, gdim)
     keep = {}
     keep["vertices"] = np.ascontiguousarray(mesh.geometry.dofmap, dtype=np.int32)  # utils.get_vertices
     keep["coords"] = np.ascontiguousarray(mesh.geometry.x, dtype=np.float64)
@@ -112,7 +181,6 @@ def assemble_matrix(form, qr_data, nthreads: int = 1, faithful: bool = False, pa
     """reference customquad/assemble_matrix.py:10-47.  Returns scipy.sparse.csr_matrix whose
     structure is the full form pattern (create_matrix(form), :19-20)."""
     import scipy.sparse as sp
-    from customquad_b200.sparsity import build_pattern
 
     assert form.rank == 2
     V = form.function_spaces[0]

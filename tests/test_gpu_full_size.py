@@ -61,7 +61,7 @@ def _sample_parity(form, qr, A, sample, oracle, bs=1):
 
 
 def _cells_pattern(form, sub):
-    from customquad_b200.sparsity import build_pattern
+    from oracle.oracle import build_pattern  # the oracle's own builder
 
     V = form.function_spaces[0]
     return build_pattern(V.dofmap.list, V.dofmap.num_dofs, V.bs, cells=sub.cells)
