@@ -1,27 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- runtime-quadrature assembly throughput on B200 (BASELINE.json metric).
 
-Workload at N=1 (BASELINE.json configs[1], SURVEY.md 8d "cfg 2"): 2-D Q1 and Q2 stiffness + mass
-matrices on a 2048x2048 quadrilateral mesh with synthetic ragged runtime quadrature, nq_c ~ U{16..64}
-points per cell, every cell listed.  One step = one pass of the hot path over that batch:
-four ``assemble_matrix`` calls (Q1 stiffness, Q1 mass, Q2 stiffness, Q2 mass), each zeroing its CSR
-values first as the reference does (assemble_matrix.py:19-20).
+Headline workload (BASELINE.json configs[1], SURVEY.md 8d "cfg 2"): 2-D Q1 and Q2 stiffness + mass matrices on a
+2048x2048 quadrilateral mesh with synthetic ragged runtime quadrature, nq_c ~ U{16..64} points per cell, every cell
+listed.  One step = one pass of the hot path over that batch: four ``assemble_matrix`` calls (Q1 stiffness, Q1 mass,
+Q2 stiffness, Q2 mass), each zeroing its CSR values first as the reference does (assemble_matrix.py:19-20).
 
     value = element tensors per second = 4 * num_cells / step time   (inputs resident in HBM)
-    e2e   = the same through cq_assemble_matrix_host: qr arrays in pinned host memory, H2D copies and
-            the D2H copy of the CSR values inside the timed region.
+    e2e   = the same through cq_assemble_matrices_host: the qr arrays start in pinned host memory, are uploaded ONCE
+            per step and serve all four forms (the reference's demo reuses one rule for a matrix and a vector,
+            demo/poisson.py:193,209); the CSR values of all four matrices come back to pinned host memory.
 
-N>1 (torchrun): the mesh grows with N (weak scaling): rank r owns the slab of 2048 cell-columns
-[r*2048, (r+1)*2048) of a (2048*N) x 2048 mesh, assembles into its own rows and ships the one
-interface dof line it does not own to rank r+1 over NCCL (customquad_b200/dist.py).
+N>1 (torchrun): the mesh grows with N (weak scaling): rank r owns the slab of 2048 cell-columns [r*2048, (r+1)*2048) of
+a (2048*N) x 2048 mesh, assembles into its own rows; the one interface dof line it does not own is added into the
+owner's matrix over NVLink by the assembly kernels themselves (customquad_b200/dist.py).  After the timed region every
+rank > 0 re-assembles the two cell layers around its interface with the CPU oracle and compares its interface rows
+(``parity``; a mismatch makes the run exit non-zero).  ``extra.config5`` (N>1) is BASELINE.json configs[4]: Q1
+hexahedra 512^3 strong-scaled over the N GPUs (bulk + cut-cell stiffness, Nitsche with normals, mass), with its own
+interface parity check.
 
-``--impl reference`` times the CPU oracle (oracle/, the restatement of the reference's numba loop +
-generated kernel: the reference itself needs dolfinx/basix/ffcx/PETSc, absent here) with all host
-threads on a bounded sample of the same workload.
+``--impl reference`` times the CPU oracle (oracle/, the restatement of the reference's numba loop + generated kernel:
+the reference itself needs dolfinx/basix/ffcx/PETSc, absent here) with all host cores on a bounded sample of the same
+workload.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -37,7 +42,9 @@ sys.path.insert(0, ROOT)
 MESH_N = 2048
 NQ_LO, NQ_HI = 16, 64
 XMIN, XMAX = [-1.11, -1.51], [1.55, 1.22]  # demo/poisson.py:42-43
+BOX3 = [[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]]  # demo/poisson.py:48-49
 FORMS = [("q1_stiffness", 1, "stiffness"), ("q1_mass", 1, "mass"), ("q2_stiffness", 2, "stiffness"), ("q2_mass", 2, "mass")]
+RTOL = 1e-12  # north_star: values within 1e-12 relative
 
 
 def log(msg):
@@ -45,11 +52,28 @@ def log(msg):
         print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
+def host_cores() -> int:
+    """Cores this process may use -- NOT omp_get_max_threads(): torch.distributed.run exports OMP_NUM_THREADS=1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_fp64():
+    """FP64 peaks from profiles/microbench/fp64_peak.cu (run on this pool's B200, profiles/r2/fp64_peak.json)."""
+    p = os.path.join(ROOT, "profiles", "r2", "fp64_peak.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["dfma_tflops"]), float(d["dmma_8x8x4_tflops"]), "measured (profiles/r2/fp64_peak.json)"
+    return 37.2, 37.2, "computed (148 SM x 64 FMA/clk x 1.965 GHz)"
 
 
 class ClockSampler:
@@ -91,16 +115,57 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows)}  # fmt: skip
 
 
-def algorithmic_bytes(num_cells, num_points, gdim, nv, n, num_nodes, nnz):
-    """per listed cell 4 (cell id) + 8 (int64 offset) + nq*8*(d+1) + 4*nv (geometry
-    dofmap) + 4*n (dofmap); + 24 per distinct geometry node; + 8*nnz output.  No credit for CSR
-    structure reads, atomics read-modify-write, or the memset."""
-    return num_cells * (4 + 8 + 4 * nv + 4 * n) + num_points * 8 * (gdim + 1) + 24 * num_nodes + 8 * nnz
+@contextlib.contextmanager
+def near_gpu(local_rank):
+    """Run a block on the cores next to GPU `local_rank` (its PCIe root / NUMA node), so that pinned host buffers
+    allocated and first touched inside it are NUMA-local to the copy engine.  No-op when sysfs has no answer."""
+    old = None
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if cpus and cpus != old:
+            os.sched_setaffinity(0, cpus)
+        else:
+            old = None
+    except Exception:  # noqa: BLE001 -- best effort
+        old = None
+    try:
+        yield
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
 
 
-def build_problem(nx, ny, rank=0, world=1):
-    """Mesh (slab `rank` of a (nx*world) x ny mesh) + spaces + synthetic ragged rule for the cells
-    this rank assembles (SURVEY.md 8d generator, seed 20231 + rank)."""
+def algorithmic_bytes(num_cells, num_points, gdim, nv, n, num_nodes, nnz, normals=False):
+    """per listed cell 4 (cell id) + 8 (int64 offset) + nq*8*(d+1 (+d with normals)) + 4*nv (geometry
+    dofmap) + 4*n (dofmap); + 24 per distinct geometry node; + 8*nnz output.  No credit for CSR structure reads,
+    atomics read-modify-write, or the memset."""
+    return num_cells * (4 + 8 + 4 * nv + 4 * n) + num_points * 8 * (gdim + 1 + (gdim if normals else 0)) + 24 * num_nodes + 8 * nnz
+
+
+def point_flops(deg, d, kind):
+    """SURVEY.md 8d "algorithmic flops per unit of work": per quadrature point, point-by-point evaluation."""
+    n, nv = (deg + 1) ** d, 2**d
+    tab = 4 * deg * d * (deg + 1) + n * (d - 1) + n * d * (d - 1)
+    geom = 2 * nv * d * d + (8 if d == 2 else 50)
+    if kind == "stiffness":
+        return tab + geom + 2 * n * d * d + 2 * n * n * d + n * d
+    return tab + geom + 2 * n * n + n
+
+
+def build_problem(nx, ny, rank=0, world=1, distort=0.0):
+    """Mesh (slab `rank` of a (nx*world) x ny mesh) + spaces + synthetic ragged rule for the cells this rank assembles
+    (SURVEY.md 8d generator, seed 20231 + rank).  distort > 0: every interior vertex is moved by up to distort*h/2 in
+    each direction (no cell of the mesh stays axis-aligned: the point-by-point kernels run)."""
     import customquad_b200 as cq
     from customquad_b200 import dist as cqdist, forms
     from customquad_b200.quadrature import synthetic_ragged
@@ -108,6 +173,16 @@ def build_problem(nx, ny, rank=0, world=1):
     hx = (XMAX[0] - XMIN[0]) / MESH_N
     slab = cqdist.make_slab([[XMIN[0], XMIN[1]], [XMIN[0] + nx * world * hx, XMAX[1]]], [nx * world, ny], rank, world)
     mesh = slab.mesh
+    if distort > 0.0:
+        x = mesh.geometry.x
+        h = mesh.h()
+        rng = np.random.default_rng(99)
+        lx, ly = mesh.shape[0] + 1, mesh.shape[1] + 1
+        interior = np.zeros((lx, ly), dtype=bool)
+        interior[1:-1, 1:-1] = True
+        interior = interior.reshape(-1)
+        x[interior, 0] += distort * h[0] * (rng.random(interior.sum()) - 0.5)
+        x[interior, 1] += distort * h[1] * (rng.random(interior.sum()) - 0.5)
     spaces = {1: cq.FunctionSpace(mesh, ("Lagrange", 1)), 2: cq.FunctionSpace(mesh, ("Lagrange", 2))}
     fl = [(name, getattr(forms, kind)(spaces[deg]), deg) for name, deg, kind in FORMS]
     qr = synthetic_ragged(slab.cells, 2, NQ_LO, NQ_HI, seed=20231 + rank)
@@ -116,7 +191,7 @@ def build_problem(nx, ny, rank=0, world=1):
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU arm: the oracle on all host threads, a bounded sample per step."""
+    """CPU arm: the oracle on all host cores, a bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -124,7 +199,7 @@ def run_reference(args):
     from oracle.oracle import build_pattern  # the oracle's own builder (oracle/cq_oracle.c)
 
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_cores()  # the same at every N (torchrun's OMP_NUM_THREADS=1 is overridden by the explicit count)
     sample_cols = int(os.environ.get("CQ_BENCH_SAMPLE_COLS", "192"))  # 192 x 2048 = 393,216 cells per step and form (~9% of the workload); the override is for tests/test_bench_contract.py
     mesh, spaces, fl, qr, _ = build_problem(sample_cols, MESH_N)
     pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
@@ -153,13 +228,16 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, kernel_path="moment", fused_zero=False):
     return {
         "workload": f"2-D Q1+Q2 stiffness+mass, {MESH_N * n_gpus}x{MESH_N} quad mesh ({MESH_N}x{MESH_N} per GPU), synthetic ragged runtime quadrature U{{{NQ_LO}..{NQ_HI}}} pts/cell, all cells listed (BASELINE.json configs[1])",
         "cells_per_gpu": MESH_N * MESH_N, "forms": [f[0] for f in FORMS], "mean_points_per_cell": (NQ_LO + NQ_HI) / 2,
         "l2": "inputs (>= 4 GB of points per pass) are larger than the 126 MB L2; no explicit flush",
         "parallelism": f"cells{n_gpus}" if n_gpus > 1 else "single",
-        "exchange": "interface rows of the neighbour rank: red.global.add.f64 into peer memory over NVLink from the assembly kernels (CQ_PEER_SCATTER=0: NCCL send/recv + accumulate kernel)" if n_gpus > 1 else "none",
+        "kernel_path": kernel_path + (" (monomial-moment kernels: every cell of the tensor mesh is axis-aligned; the general-cell point-by-point path is timed in extra.general_cells)" if kernel_path == "moment" else " (point-by-point kernels)"),
+        "zeroing": "in-kernel (cq_ctx_set_fused_zero)" if fused_zero else "memset before the kernel",
+        "parity_pinned_by_reference_tests": "Q1 mass-type only (test/test_linear_basis.py); Q1/Q2 stiffness and Q2 mass are pinned by sympy closed forms and the demo's convergence (DESIGN.md 6)",
+        "exchange": "interface rows of the neighbour rank: red.global.add.f64 into peer memory over NVLink from the assembly kernels, neighbour fences through peer-memory flags (CQ_PEER_SCATTER=0: ncclSend/ncclRecv + accumulate kernel, cq_exchange_offrank)" if n_gpus > 1 else "none",
     }  # fmt: skip
 
 
@@ -168,7 +246,7 @@ def cpu_baseline_sample():
     from oracle import oracle
     from oracle.oracle import build_pattern  # the oracle's own builder (oracle/cq_oracle.c)
 
-    threads = oracle.max_threads()
+    threads = host_cores()
     cols = 512  # 512 x 2048 = 1,048,576 cells (a quarter of the workload), all 4 forms once
     mesh, spaces, fl, qr, _ = build_problem(cols, MESH_N)
     pats = {d: build_pattern(V.dofmap.list, V.dofmap.num_dofs) for d, V in spaces.items()}
@@ -184,10 +262,333 @@ def cpu_baseline_sample():
     for _, form, deg in fl:
         oracle.assemble_matrix(form, [q1], nthreads=1, pattern=pats[deg])
     dt1 = time.perf_counter() - t1
+    # structure-faithful flavour: call_basix rebuilds heap tables per cell and per table like call_basix.h:49-57
+    nf = 32 * MESH_N
+    qf = qr.select(np.arange(nf))
+    t2 = time.perf_counter()
+    for _, form, deg in fl:
+        oracle.assemble_matrix(form, [qf], nthreads=threads, faithful=True, pattern=pats[deg])
+    dt2 = time.perf_counter() - t2
     return {"value": len(fl) * mesh.num_cells / dt, "unit": "element tensors/s", "cores": threads, "kind": "port", "seconds": dt,
             "sample": f"{cols}x{MESH_N} cell slab ({mesh.num_cells} cells, {qr.num_points} points) of the workload, all 4 forms once; oracle/cq_oracle.c allocation-free flavour, OpenMP over cells",
             "single_core": {"value": len(fl) * n1 / dt1, "unit": "element tensors/s", "cores": 1, "seconds": dt1,
-                            "sample": f"64x{MESH_N} cell slab ({n1} cells, {q1.num_points} points), all 4 forms once"}}  # fmt: skip
+                            "sample": f"64x{MESH_N} cell slab ({n1} cells, {q1.num_points} points), all 4 forms once"},
+            "structure_faithful": {"value": len(fl) * nf / dt2, "unit": "element tensors/s", "cores": threads, "seconds": dt2,
+                                   "sample": f"32x{MESH_N} cell slab ({nf} cells), all 4 forms once; heap basis tables rebuilt per cell and table (call_basix.h:49-57 allocation pattern; basix::create_element itself cannot be reproduced)"}}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+def compare_interface_rows(A, R, r0, r1):
+    """Rows [r0, r1) of the device matrix A against the same rows of the oracle's scipy matrix R (built on the pattern
+    of the cells around the interface: for these rows that is the full pattern).  Returns (rows, max_rel, ok)."""
+    ip = A.indptr[r0 : r1 + 1].cpu().numpy()
+    lo, hi = int(ip[0]), int(ip[-1])
+    idx = A.indices[lo:hi].cpu().numpy()
+    val = A.data[lo:hi].cpu().numpy()
+    rip = R.indptr[r0 : r1 + 1].astype(np.int64)
+    ridx = R.indices[rip[0] : rip[-1]]
+    rval = R.data[rip[0] : rip[-1]]
+    same_pattern = np.array_equal(ip - ip[0], rip - rip[0]) and np.array_equal(idx, ridx)
+    if not same_pattern:
+        return r1 - r0, float("inf"), False
+    scale = float(np.max(np.abs(rval))) if rval.size else 1.0
+    err = float(np.max(np.abs(val - rval))) / scale if rval.size else 0.0
+    nerr = float(np.linalg.norm(val - rval) / max(np.linalg.norm(rval), 1e-300))
+    return r1 - r0, max(err, nerr), err <= RTOL and nerr <= RTOL
+
+
+def cat_rules(a, b):
+    """Two host rules one after the other."""
+    from customquad_b200.quadrature import RaggedQuadrature
+
+    off = np.concatenate([a.offsets, a.offsets[-1] + b.offsets[1:]])
+    n = None if a.n is None else np.concatenate([a.n, b.n])
+    return RaggedQuadrature(np.concatenate([a.cells, b.cells]).astype(np.int32), off, np.concatenate([a.pts, b.pts]), np.concatenate([a.w, b.w]), n, a.gdim)
+
+
+def interface_parity_cfg2(rank, world, slab, fl, mats, exch, qr):
+    """Every rank > 0: oracle on its ghost cell layer (the neighbour's top layer, rule regenerated from the neighbour's
+    seed) + its own first layer; compare the owned interface rows of all four matrices."""
+    from customquad_b200 import dist as cqdist
+    from customquad_b200.quadrature import synthetic_ragged
+    from oracle import oracle
+
+    if rank == 0:
+        return {"rows": 0, "max_rel": 0.0, "ok": True}
+    per_layer = MESH_N
+    hx = (XMAX[0] - XMIN[0]) / MESH_N
+    nb = cqdist.make_slab([[XMIN[0], XMIN[1]], [XMIN[0] + MESH_N * world * hx, XMAX[1]]], [MESH_N * world, MESH_N], rank - 1, world)
+    nbq = synthetic_ragged(nb.cells, 2, NQ_LO, NQ_HI, seed=20231 + rank - 1)
+    top = nbq.select(np.arange(nbq.num_entries - per_layer, nbq.num_entries))
+    top.cells = np.arange(per_layer, dtype=np.int32)  # the neighbour's top layer is this rank's ghost layer (local cells 0..)
+    own = qr.select(np.arange(per_layer))
+    rule = cat_rules(top, own)
+    rows, worst, ok = 0, 0.0, True
+    for name, form, _deg in fl:
+        V = form.function_spaces[0]
+        pat = oracle.build_pattern(V.dofmap.list, V.dofmap.num_dofs, V.bs, cells=rule.cells)
+        R = oracle.assemble_matrix(form, [rule], nthreads=host_cores(), pattern=pat)
+        ex = exch[name]
+        n, e, good = compare_interface_rows(mats[name], R, ex.recv_row0, ex.recv_row0 + ex.line)
+        rows, worst, ok = rows + n, max(worst, e), ok and good
+    return {"rows": int(rows), "max_rel": worst, "ok": bool(ok)}
+
+
+# ------------------------------------------------------------------------------------------------
+def config5_leg(args, rank, world, dev, peak):
+    """BASELINE.json configs[4]: full bulk + cut runtime-quadrature assembly, Q1 hexahedra 512^3, cell-partitioned
+    (strong scaling) over the N GPUs with the off-rank row exchange.  Unit sphere level set (demo/sphere.hpp): cells
+    cut by the surface get U{8..27} bulk points and a surface rule of U{4..16} points with normals, all other cells the
+    fixed 8-point rule.  One step: A <- 0; A += stiffness(all cells); A += Nitsche(cut cells); M <- 0; M += mass(all
+    cells); interface rows of both matrices exchanged.  The rules are generated on the device."""
+    import torch
+    import torch.distributed as dist
+
+    import customquad_b200 as cq
+    from customquad_b200 import assemble as asm
+    from customquad_b200 import dist as cqdist, forms
+    from customquad_b200.quadrature import RaggedQuadrature
+
+    N5 = int(os.environ.get("CQ_BENCH_C5_N", "512"))
+    lo, hi = np.asarray(BOX3[0]), np.asarray(BOX3[1])
+    log(f"config 5: classification of {N5}^3 cells")
+    # cut cells per z-layer (device, every rank the same): phi = |x|^2 - 1 at the vertices
+    ax = [torch.linspace(lo[d], hi[d], N5 + 1, dtype=torch.float64, device=dev) for d in range(3)]
+
+    def cut_mask(z0, z1):  # cells of layers [z0, z1): [nz, ny, nx] bool
+        ins = (ax[2][z0 : z1 + 1, None, None] ** 2 + ax[1][None, :, None] ** 2 + ax[0][None, None, :] ** 2) < 1.0
+        cnt = torch.zeros((z1 - z0, N5, N5), dtype=torch.int8, device=dev)
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    cnt += ins[dz : dz + z1 - z0, dy : dy + N5, dx : dx + N5].to(torch.int8)
+        return (cnt > 0) & (cnt < 8)
+
+    per_layer_cut = torch.cat([cut_mask(z, min(z + 32, N5)).sum(dim=(1, 2)) for z in range(0, N5, 32)]).cpu().numpy()
+    # work per layer ~ sum of nq * n^2 (SURVEY 8e): 8 points per cell, cut cells 17.5 + 10 (surface) on average
+    weights = (N5 * N5 - per_layer_cut) * 8.0 + per_layer_cut * 27.5
+    bounds = cqdist.partition_layers(N5, world, weights=weights)
+    slab = cqdist.make_slab(BOX3, [N5, N5, N5], rank, world, bounds=bounds)
+    mesh = slab.mesh
+    per_layer = N5 * N5
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    log(f"config 5: slab of {slab.count} layers ({len(slab.cells)} cells) on rank 0, bounds {list(map(int, bounds))}")
+    # ---- rules, born on the device -------------------------------------------------------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(5150 + rank)
+    C = len(slab.cells)
+    cells_t = torch.arange(slab.ghost * per_layer, slab.ghost * per_layer + C, dtype=torch.int32, device=dev)
+    cut = cut_mask(slab.first, slab.first + slab.count).reshape(-1)
+    cut_idx = torch.nonzero(cut).reshape(-1)
+    ncut = int(cut_idx.shape[0])
+    nq = torch.full((C,), 8, dtype=torch.int64, device=dev)
+    nq[cut_idx] = torch.randint(8, 28, (ncut,), generator=g, device=dev)
+    off = torch.zeros(C + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(nq, 0)
+    P = int(off[-1])
+    pts = torch.rand(3 * P, dtype=torch.float64, device=dev, generator=g)
+    w = torch.rand(P, dtype=torch.float64, device=dev, generator=g).add_(0.5)
+    w.div_(torch.repeat_interleave(nq.to(torch.float64), nq))
+    q_bulk = RaggedQuadrature.on_device(cells_t, off, pts, w, None, 3)
+    nqs = torch.randint(4, 17, (ncut,), generator=g, device=dev)
+    offs = torch.zeros(ncut + 1, dtype=torch.int64, device=dev)
+    offs[1:] = torch.cumsum(nqs, 0)
+    Ps = int(offs[-1])
+    nrm = torch.randn((Ps, 3), dtype=torch.float64, device=dev, generator=g)
+    nrm = (nrm / nrm.norm(dim=1, keepdim=True)).reshape(-1)
+    ws = torch.rand(Ps, dtype=torch.float64, device=dev, generator=g).add_(0.5)
+    ws.div_(torch.repeat_interleave(nqs.to(torch.float64), nqs))
+    q_surf = RaggedQuadrature.on_device(cells_t[cut_idx].contiguous(), offs, torch.rand(3 * Ps, dtype=torch.float64, device=dev, generator=g), ws, nrm, 3)
+    del cut, nq, nqs
+    # ---- matrices, exchange -----------------------------------------------------------------------
+    f_stiff, f_nit, f_mass = forms.stiffness(V), forms.nitsche(V, 10.0), forms.mass(V)
+    log("config 5: sparsity pattern + scatter map")
+    A, M = asm.create_matrix(f_stiff), asm.create_matrix(f_mass)
+    exA, exM = cqdist.SlabExchange(V, slab), cqdist.SlabExchange(V, slab)
+    exA.set_pattern(A.indptr, A.indices)
+    exM.set_pattern(M.indptr, M.indices)
+    fused = os.environ.get("CQ_PEER_SCATTER", "1") != "0" and all([exA.enable_peer_scatter(A), exM.enable_peer_scatter(M)])
+    state = {"fused": fused}
+
+    def step(timers=None):
+        for mat, ex, work in ((A, exA, ((f_stiff, q_bulk), (f_nit, q_surf))), (M, exM, ((f_mass, q_bulk),))):
+            mat.data.zero_()  # A.zeroEntries()
+            if state["fused"]:
+                ex.fence(dev)  # every rank's matrix is zeroed before any rank's kernel adds into a neighbour
+            for form, q in work:
+                asm.assemble_matrix(form, [q], A=mat)
+            if timers is not None:
+                timers.append(torch.cuda.Event(enable_timing=True))
+                timers[-1].record()
+            ex.exchange_matrix(mat.data)  # fused: completion fence; else ncclSend/ncclRecv + accumulate
+            if timers is not None:
+                timers.append(torch.cuda.Event(enable_timing=True))
+                timers[-1].record()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(reps):
+        timers = []
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for _ in range(reps):
+            step(timers)
+        t1.record()
+        barrier()
+        v = torch.tensor([t0.elapsed_time(t1) / reps, sum(timers[i].elapsed_time(timers[i + 1]) for i in range(0, len(timers), 2)) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v[0]), float(v[1])
+
+    log("config 5: warm-up")
+    for _ in range(2):
+        step()
+    A.assemble()
+    ms_step, ms_exchange = timed(max(2, min(args.steps, 3)))
+    # the same step with the NCCL exchange (cq_exchange_offrank), for the record
+    ms_nccl = None
+    if fused:
+        saved = [(m.peer_row0, m.peer_rowstart, m.peer_target, m.peer_exchange) for m in (A, M)]
+        for m, ex in ((A, exA), (M, exM)):
+            m.peer_row0, m.peer_rowstart, m.peer_target, m.peer_exchange, ex.peer = None, None, False, None, False
+        state["fused"] = False
+        step()
+        a, b = timed(2)
+        ms_nccl = {"ms_per_step": a, "exchange_ms": b}
+        for (m, ex), sv in zip(((A, exA), (M, exM)), saved):
+            m.peer_row0, m.peer_rowstart, m.peer_target, m.peer_exchange = sv
+            ex.peer = True
+        state["fused"] = True
+        step()  # the matrices checked below come from the fused path
+        barrier()
+    # ---- parity on the interface: oracle on the ghost layer (the neighbour's rule, sent up) + own first layer ----
+    log("config 5: interface parity against the oracle")
+
+    def layer_slice(q, first_cell, ncells):  # host rule of the entries whose cell lies in [first_cell, first_cell + ncells)
+        _, (c, o, p_, w_, n_) = q.device_arrays()
+        k = torch.nonzero((c >= first_cell) & (c < first_cell + ncells)).reshape(-1)
+        if k.numel() == 0:
+            e = np.zeros(0)
+            return RaggedQuadrature(np.zeros(0, np.int32), np.zeros(1, np.int64), e, e, None if n_ is None else e, 3)
+        k0, k1 = int(k[0]), int(k[-1]) + 1  # entries are cell-ascending: a contiguous range
+        p0, p1 = int(o[k0]), int(o[k1])
+        hn = None if n_ is None else n_[3 * p0 : 3 * p1].cpu().numpy()
+        return RaggedQuadrature(c[k0:k1].cpu().numpy(), (o[k0 : k1 + 1] - p0).cpu().numpy(), p_[3 * p0 : 3 * p1].cpu().numpy(), w_[p0:p1].cpu().numpy(), hn, 3)
+
+    top_cell = (slab.ghost + slab.count - 1) * per_layer
+    mine_up = [layer_slice(q, top_cell, per_layer) for q in (q_bulk, q_surf)]
+    for r in mine_up:
+        r.cells = (r.cells - top_cell).astype(np.int32)  # the receiver's ghost layer is its local cells 0..per_layer-1
+    got = [None] * world
+    dist.all_gather_object(got, None if rank == world - 1 else [(r.cells, r.offsets, r.pts, r.w, r.n) for r in mine_up])
+    par = {"rows": 0, "max_rel": 0.0, "ok": True}
+    if rank > 0:
+        from oracle import oracle
+
+        below = [RaggedQuadrature(*t, 3) for t in got[rank - 1]]
+        own = [layer_slice(q, slab.ghost * per_layer, per_layer) for q in (q_bulk, q_surf)]
+        rule_bulk, rule_surf = cat_rules(below[0], own[0]), cat_rules(below[1], own[1])
+        pat = oracle.build_pattern(V.dofmap.list, V.dofmap.num_dofs, 1, cells=np.arange(2 * per_layer, dtype=np.int32))
+        T = host_cores()
+        RA = oracle.assemble_matrix(f_stiff, [rule_bulk], nthreads=T, pattern=pat)
+        if rule_surf.num_entries:
+            RA.data += oracle.assemble_matrix(f_nit, [rule_surf], nthreads=T, pattern=pat).data  # same pattern object: same slots
+        RM = oracle.assemble_matrix(f_mass, [rule_bulk], nthreads=T, pattern=pat)
+        rows, worst, ok = 0, 0.0, True
+        for mat, R, ex in ((A, RA, exA), (M, RM, exM)):
+            n_, e_, g_ = compare_interface_rows(mat, R, ex.recv_row0, ex.recv_row0 + ex.line)
+            rows, worst, ok = rows + n_, max(worst, e_), ok and g_
+        par = {"rows": int(rows), "max_rel": worst, "ok": bool(ok)}
+    del got
+    allp = [None] * world
+    dist.all_gather_object(allp, par)
+    # ---- bookkeeping ---------------------------------------------------------------------------------
+    nodes = mesh.geometry.x.shape[0]
+    ab = (algorithmic_bytes(C, P, 3, 8, 8, nodes, A.nnz) + algorithmic_bytes(ncut, Ps, 3, 8, 8, 0, 0, normals=True)
+          + algorithmic_bytes(C, P, 3, 8, 8, nodes, M.nnz))  # fmt: skip
+    tot = torch.tensor([float(C), float(ncut), float(P + Ps), float(ab)], device=dev, dtype=torch.float64)
+    mx = tot.clone()
+    dist.all_reduce(tot)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    iface = (N5 + 1) ** 2
+    return {
+        "workload": f"Q1 hex {N5}^3, strong scaling over {world} GPUs (work-balanced z-slabs): stiffness on all cells (8 pts, cut cells U{{8..27}}) + Nitsche with normals on the cut cells (U{{4..16}}) into A, mass on all cells into M; unit-sphere level set, rules generated on the device (BASELINE.json configs[4])",
+        "cells": int(tot[0]), "cut_cells": int(tot[1]), "points": int(tot[2]), "ms_per_step": ms_step,
+        "element_tensors_per_s": (2 * float(tot[0]) + float(tot[1])) / (ms_step * 1e-3),
+        "csr_nnz_per_s": 2.0 * 27 * (N5 + 1) ** 3 / (ms_step * 1e-3),
+        "exchange": "fused: red.global.add.f64 into the owner's memory over NVLink + two fences per matrix" if fused else "ncclSend/ncclRecv of the interface rows + accumulate kernel (cq_exchange_offrank)",
+        "exchange_ms": ms_exchange, "interface_rows": iface, "interface_bytes_per_matrix": iface * 18 * 8,
+        "nccl_exchange_path": ms_nccl,
+        "per_gpu_roofline": {"bound": "hbm", "algorithmic_bytes_max_rank": float(mx[3]), "achieved_gbs": float(mx[3]) / ms_step / 1e6, "peak": peak,
+                             "frac": float(mx[3]) / ms_step / 1e6 / peak},
+        "partition": {"bounds": [int(b) for b in bounds], "max_cells_per_rank": int(mx[0])},
+        "parity": {"checked": True, "rows": int(sum(p["rows"] for p in allp)), "max_rel": max(p["max_rel"] for p in allp), "ok": all(p["ok"] for p in allp),
+                   "what": "owned interface rows of A and M on every rank > 0 vs the CPU oracle on the two cell layers around the interface"},
+        "parity_pinned_by_reference_tests": "Q1 hexahedron mass (test/test_linear_basis.py:41-66); stiffness and Nitsche/normals are pinned by sympy closed forms (DESIGN.md 6)",
+    }  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+def general_cells_leg(dev, peak):
+    """The headline workload on a DISTORTED mesh: no cell is axis-aligned, cq_mesh_classify says so, and the same four
+    assemble_matrix calls run the point-by-point staged kernels (MODE 0) instead of the moment kernels."""
+    import torch
+
+    from customquad_b200 import assemble as asm
+
+    mesh, spaces, fl, qr, _ = build_problem(MESH_N, MESH_N, distort=0.3)
+    asm.qr_on_device(qr, dev)
+    dfma, _dmma, src = measured_fp64()
+    out = {"mesh": "2048x2048 quadrilaterals, every interior vertex moved by up to 0.15 h in x and y (seeded): bilinear, non-affine cells",
+           "kernel_path": "point (assemble_staged_kernel MODE 0)", "fp64_peak_tflops": dfma, "fp64_peak_source": src, "per_kernel": []}
+    assert not (asm.mesh_on_device(mesh, dev)[2] & 1), "the distorted mesh was classified axis-aligned"
+    total = 0.0
+    for name, form, deg in fl:
+        A = asm.create_matrix(form)
+        ts = []
+        for _ in range(4):
+            A.data.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            asm.assemble_matrix(form, [qr], A=A)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        A.assemble()
+        ms = float(np.mean(ts[1:]))
+        total += ms
+        ab = algorithmic_bytes(qr.num_entries, qr.num_points, 2, 4, (deg + 1) ** 2, mesh.geometry.x.shape[0], A.nnz)
+        fl_ = point_flops(deg, 2, name.split("_")[1]) * qr.num_points
+        t_hbm, t_f64 = ab / (peak * 1e6), fl_ / (dfma * 1e9)  # ms
+        out["per_kernel"].append({"kernel": name, "ms": ms, "frac_hbm": t_hbm / ms, "frac_fp64": t_f64 / ms, "bound": "fp64" if t_f64 > t_hbm else "hbm",
+                                  "frac_binding": max(t_hbm, t_f64) / ms, "algorithmic_flops": fl_})  # fmt: skip
+        del A
+    out["ms_per_step_kernels"] = total
+    out["element_tensors_per_s"] = len(fl) * qr.num_entries / (total * 1e-3)
+    qr._dev.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def list_input_leg(qr):
+    """The reference's own input form: lists of per-cell arrays (demo/poisson.py:109-113).  Time of normalising the
+    full 4.2 M-cell rule into the flat ragged arrays (customquad_b200/quadrature.py; csrc/cq_pyflatten.c)."""
+    from customquad_b200.quadrature import _flatten_helper, normalise_qr
+
+    off = qr.offsets
+    t0 = time.perf_counter()
+    pts = [qr.pts[2 * off[k] : 2 * off[k + 1]] for k in range(qr.num_entries)]
+    w = [qr.w[off[k] : off[k + 1]] for k in range(qr.num_entries)]
+    t_make = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    q = normalise_qr((qr.cells, pts, w), 2)
+    dt = time.perf_counter() - t0
+    ok = bool(np.array_equal(q.offsets, off) and np.array_equal(q.w, qr.w) and np.array_equal(q.pts, qr.pts))
+    return {"seconds": dt, "cells": int(qr.num_entries), "ns_per_cell": dt / qr.num_entries * 1e9, "identical_to_flat_rule": ok,
+            "helper": "csrc/cq_pyflatten.c" if _flatten_helper() is not None else "numpy (helper not built)",
+            "note": f"once per rule, outside the timed e2e region (building the {qr.num_entries} Python arrays themselves took {t_make:.1f} s)"}  # fmt: skip
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,11 +609,14 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    if args.fused_zero:
+        asm.set_fused_zero(True)
 
     log("building problem")
     mesh, spaces, fl, qr, slab = build_problem(MESH_N, MESH_N, rank, world)
     C_cells, P_pts = qr.num_entries, qr.num_points
     mats = {name: asm.create_matrix(form) for name, form, _ in fl}
+    kernel_path = "moment" if (asm.mesh_on_device(mesh, dev)[2] & 1) else "point"
     exch = None
     if world > 1:
         from customquad_b200 import dist as cqdist
@@ -228,7 +632,7 @@ def run_gpu(args):
             fused = all([exch[name].enable_peer_scatter(mats[name]) for name, _, _ in fl])
             if not fused:
                 for name in mats:
-                    mats[name].peer_row0, mats[name].peer_rowstart = None, None
+                    mats[name].peer_row0, mats[name].peer_rowstart, mats[name].peer_target, mats[name].peer_exchange = None, None, False, None
                     exch[name].peer = False
             log(f"interface exchange: {'peer RED over NVLink (fused in the assembly kernels)' if fused else 'NCCL send/recv'}")
     asm.qr_on_device(qr, dev)  # inputs resident in HBM before the timed region
@@ -239,12 +643,9 @@ def run_gpu(args):
             A = mats[name]
             if events is not None:
                 events[i][0].record()
-            if fused:
-                A.data.zero_()  # A.zeroEntries() (assemble_matrix.py:20)
-                exch[name].fence(dev)  # the neighbour's kernel adds into this matrix: it must be zeroed first
-                asm.assemble_matrix(form, [qr], A=A)
-            else:
-                asm.assemble_matrix(form, [qr], A=A, zero=True)  # A.zeroEntries() + assembly in one call (cq_assemble_matrix_zero)
+            # A.zeroEntries() (assemble_matrix.py:20) + assembly: cq_assemble_matrix_zero; with the peer scatter the call
+            # zeroes, fences with the neighbours (their kernels add into this matrix), then assembles
+            asm.assemble_matrix(form, [qr], A=A, zero=True)
             if exch is not None:
                 exch[name].exchange_matrix(A.data)  # fused: only the completion fence
             if events is not None:
@@ -284,8 +685,18 @@ def run_gpu(args):
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_step = ms_total / args.steps
     per_form_ms = [float(np.mean([ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)])) for i in range(len(fl))]
-
     log(f"timed region done: {ms_step:.3f} ms/step")
+
+    # ---- multi-GPU parity: the matrices of the last timed step against the oracle around every interface ----
+    parity = None
+    if world > 1:
+        log("interface parity against the oracle")
+        mine = interface_parity_cfg2(rank, world, slab, fl, mats, exch, qr)
+        allp = [None] * world
+        dist.all_gather_object(allp, mine)
+        parity = {"checked": True, "rows": int(sum(p["rows"] for p in allp)), "max_rel": max(p["max_rel"] for p in allp), "ok": all(p["ok"] for p in allp),
+                  "what": "owned interface rows of the 4 matrices on every rank > 0 (result of the last timed step, exchange included) vs the CPU oracle on the two cell layers around the interface; sparsity bit-exact, values to 1e-12"}  # fmt: skip
+
     # ---- per-kernel roofline (kernel-only times: separate pass, events around the launch alone) ----
     peak, peak_src = measured_peak()
     kern = []
@@ -294,10 +705,14 @@ def run_gpu(args):
         ts = []
         for _ in range(max(3, args.steps)):
             A.data.zero_()
+            if fused:
+                exch[name].fence(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             asm.assemble_matrix(form, [qr], A=A)
             e1.record()
+            if fused:
+                exch[name].fence(dev)
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = float(np.mean(ts))
@@ -313,14 +728,17 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "per_kernel": kern}  # fmt: skip
 
-    # ---- end to end: host (pinned) qr buffers in, CSR values out to pinned host memory --------------
+    # ---- end to end: host (pinned) qr buffers in ONCE per step, CSR values of all four matrices out ----
     e2e = None
     if not args.no_e2e:
         log("e2e: pinning host buffers")
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-        hq = RaggedQuadrature(pin(qr.cells), pin(qr.offsets), pin(qr.pts), pin(qr.w), None, 2)
+        with near_gpu(local_rank):
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+            hq = RaggedQuadrature(pin(qr.cells), pin(qr.offsets), pin(qr.pts), pin(qr.w), None, 2)
+            vals = {name: torch.empty(mats[name].nnz, dtype=torch.float64).pin_memory() for name in mats}
+            for v in vals.values():
+                v.zero_()  # first touch on the local node
         hq_np = RaggedQuadrature(hq.cells.numpy(), hq.offsets.numpy(), hq.pts.numpy(), hq.w.numpy(), None, 2)
-        vals = {name: torch.empty(mats[name].nnz, dtype=torch.float64).pin_memory() for name in mats}
 
         iface = {}
         if exch is not None:
@@ -328,22 +746,23 @@ def run_gpu(args):
                 ex = exch[name]
                 ip = mats[name].indptr[ex.recv_row0 : ex.recv_row0 + ex.line + 1 : ex.line].cpu().numpy() if ex.has_down else [0, 0]
                 iface[name] = (int(ip[0]), int(ip[-1]))
-        saved = {name: (mats[name].peer_row0, mats[name].peer_rowstart) for name in mats}
+        saved = {name: (mats[name].peer_row0, mats[name].peer_rowstart, mats[name].peer_target, mats[name].peer_exchange) for name in mats}
         for name in mats:  # the host-buffer call zeroes inside the call: it uses the NCCL exchange
-            mats[name].peer_row0, mats[name].peer_rowstart = None, None
+            mats[name].peer_row0, mats[name].peer_rowstart, mats[name].peer_target, mats[name].peer_exchange = None, None, False, None
+        names = [name for name, _, _ in fl]
 
         def e2e_step():
-            for name, form, _ in fl:
-                asm.assemble_matrix_host(form, hq_np, mats[name], vals[name])
-                if exch is not None:
-                    # the neighbour's contributions to this rank's interface rows arrive after the call's own D2H:
-                    # refresh those rows of the host copy (one lattice line, ~100 kB)
+            asm.assemble_matrices_host([f for _, f, _ in fl], hq_np, [mats[n] for n in names], [vals[n] for n in names])
+            if exch is not None:
+                # the neighbour's contributions to this rank's interface rows arrive after the call's own D2H:
+                # refresh those rows of the host copy (one lattice line, ~100 kB)
+                for name in names:
                     ex = exch[name]
                     ex.exchange_matrix(mats[name].data, force_nccl=True)
                     if ex.has_down:
                         lo, hi = int(iface[name][0]), int(iface[name][1])
                         vals[name][lo:hi].copy_(mats[name].data[lo:hi], non_blocking=True)
-                        torch.cuda.current_stream().synchronize()
+                torch.cuda.current_stream().synchronize()
 
         log("e2e: warm-up")
         for _ in range(2):
@@ -360,13 +779,32 @@ def run_gpu(args):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the host copy of the last e2e step against the device result it was copied from
+        chk = float((vals[names[-1]][:1000000].to(dev) - mats[names[-1]].data[:1000000]).abs().max())
         for name in mats:
-            mats[name].peer_row0, mats[name].peer_rowstart = saved[name]
-        h2d = len(fl) * (qr.cells.nbytes + qr.offsets.nbytes + qr.pts.nbytes + qr.w.nbytes)
+            mats[name].peer_row0, mats[name].peer_rowstart, mats[name].peer_target, mats[name].peer_exchange = saved[name]
+        h2d = qr.cells.nbytes + qr.offsets.nbytes + qr.pts.nbytes + qr.w.nbytes
         d2h = sum(8 * mats[name].nnz for name in mats) + sum(8 * (hi - lo) for lo, hi in iface.values())
         e2e = {"value": len(fl) * C_cells * world / dt, "unit": "element tensors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt * 1e3, "api": "cq_assemble_matrix_host (pinned host qr in, CSR values out)"}  # fmt: skip
+               "ms_per_step": dt * 1e3, "host_copy_max_abs_diff_vs_device": chk,
+               "api": "cq_assemble_matrices_host: the pinned host rule is uploaded once per step (8 chunks overlapping the kernels) and serves all 4 forms; finished CSR rows of every matrix stream back while later chunks upload"}  # fmt: skip
+        del hq, hq_np, vals
 
+    extra = {}
+    if world > 1 and os.environ.get("CQ_BENCH_C5", "1") != "0" and not args.no_extra:
+        # free the headline problem first
+        for name in list(mats):
+            del mats[name]
+        exch = None
+        qr._dev.clear()
+        torch.cuda.empty_cache()
+        try:
+            extra["config5"] = config5_leg(args, rank, world, dev, peak)
+        except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+            import traceback
+
+            traceback.print_exc()
+            extra["config5"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -377,20 +815,44 @@ def run_gpu(args):
         log("cpu baseline sample")
         cpu = cpu_baseline_sample()
         log("cpu baseline done")
+    if world == 1 and not args.no_extra:
+        log("extra: general (distorted) cells, list-of-arrays input")
+        for name in list(mats):
+            del mats[name]
+        torch.cuda.empty_cache()
+        try:
+            extra["list_input"] = list_input_leg(qr)
+            qr._dev.clear()
+            extra["general_cells"] = general_cells_leg(dev, peak)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc()
+            extra["error"] = f"{type(e).__name__}: {e}"[:300]
+    dfma, dmma, fsrc = measured_fp64()
     line = {
         "metric": "element_tensors_per_s", "value": len(fl) * C_cells * world / (ms_step * 1e-3), "unit": "element tensors/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-        "csr_nnz_per_s": sum(mats[n].nnz for n in mats) * world / (ms_step * 1e-3),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, kernel_path, args.fused_zero),
+        "csr_nnz_per_s": sum(k["nnz"] for k in kern) * world / (ms_step * 1e-3),
         "per_form_ms": dict(zip([f[0] for f in fl], per_form_ms)),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "fp64_peak": {"dfma_tflops": dfma, "dmma_8x8x4_tflops": dmma, "source": fsrc},
     }  # fmt: skip
+    if parity is not None:
+        line["parity"] = parity
+    if extra:
+        line["extra"] = extra
     # flush before any teardown: stdout is block-buffered when redirected, and a line lost to a late
     # failure (seen once: an empty output file from a 4-GPU run whose timed region had finished) is a lost run
     emit(line)
+    bad = (parity is not None and not parity["ok"]) or (isinstance(extra.get("config5"), dict) and extra["config5"].get("parity", {}).get("ok") is False)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if bad:
+        log("PARITY FAILURE at the partition interfaces")
+        sys.exit(3)
 
 
 _JSON_FD = None
@@ -416,6 +878,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (N=1: general cells, list input; N>1: config 5, also CQ_BENCH_C5=0)")
+    ap.add_argument("--fused-zero", action="store_true", help="zero the matrices inside the moment kernels (cq_ctx_set_fused_zero)")
     ap.add_argument("--forms", default="", help="development only: comma-separated subset of the workload's forms (changes the workload; shown in config.forms)")
     args = ap.parse_args()
     if args.forms:

@@ -110,8 +110,11 @@ def coefficient_on_device(f, dev):
 
 
 def qr_on_device(q: RaggedQuadrature, dev):
+    """The device copy of a rule, made once and kept on the rule object: every later assemble_* call over the same
+    rule (another form, another space, the right-hand side) reuses it -- the device-resident handle of the qr tuple."""
     torch = _torch()
     if dev not in q._dev:
+        assert q.cells is not None, f"this rule lives on {q.device_arrays()[0]}, not on {dev}"
         up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
         q._dev[dev] = (up(q.cells), up(q.offsets), up(q.pts), up(q.w), up(q.n))
     return q._dev[dev]
@@ -127,10 +130,11 @@ class _Call:
         self.q = normalise_qr(qr, gdim)
         q = self.q
         if q.num_entries and q._dev.get("checked_cells") != mesh.num_cells:  # validated once per rule
-            assert int(q.cells.min()) >= 0 and int(q.cells.max()) < mesh.num_cells, "cell index out of range"
+            cells = q.cells if q.cells is not None else q.device_arrays()[1][0]
+            assert int(cells.min()) >= 0 and int(cells.max()) < mesh.num_cells, "cell index out of range"
             q._dev["checked_cells"] = mesh.num_cells
         if form.kind.name.startswith("NITSCHE"):
-            assert q.n is not None, "this form needs normals: pass (cells, qr_pts, qr_w, qr_n)"
+            assert q.has_normals, "this form needs normals: pass (cells, qr_pts, qr_w, qr_n)"
         self.keep = []
         gd, xc, mflags = mesh_on_device(mesh, dev)
         self.mesh = _lib.MeshDesc(mesh.num_cells, mesh.geometry.x.shape[0], _ptr(gd), _ptr(xc), mflags)
@@ -147,6 +151,7 @@ class _Call:
         self._consts = (C.c_double * max(1, consts.size))(*consts.tolist())
         self.form = _lib.FormDesc(int(form.kind), int(mesh.cell_type), int(form.degree), int(form.bs), int(form.fn_kind), int(consts.size), self._consts)
         if host_qr:
+            q = q.host()
             arrs = (q.cells, q.offsets, q.pts, q.w, q.n)
             hp = lambda a: None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())  # noqa: E731
             self.keep += list(arrs)

@@ -49,7 +49,25 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-ldl"])
+    build_flatten(force)
     return LIB
+
+
+FLATTEN_SO = os.path.join(HERE, "_cq_flatten.so")
+
+
+def build_flatten(force: bool = False) -> str:
+    """The CPython helper that flattens the reference's lists of per-cell arrays (csrc/cq_pyflatten.c), gcc, in-tree."""
+    import sysconfig
+
+    import numpy
+
+    src = os.path.join(CSRC, "cq_pyflatten.c")
+    if force or not os.path.exists(FLATTEN_SO) or os.path.getmtime(FLATTEN_SO) < os.path.getmtime(src):
+        tmp = f"{FLATTEN_SO}.{os.getpid()}.tmp"
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", f"-I{sysconfig.get_paths()['include']}", f"-I{numpy.get_include()}", src, "-o", tmp], check=True)
+        os.replace(tmp, FLATTEN_SO)
+    return FLATTEN_SO
 
 
 if __name__ == "__main__":

@@ -145,6 +145,12 @@ class FunctionSpace:
 def _build_dofmap(mesh: Mesh, degree: int) -> tuple[np.ndarray, int, tuple]:
     k = degree
     r = reference_lattice(mesh.cell_type, k)  # cell frame
+    if k == 1:
+        # degree 1: dofs are numbered like the vertices, in the same sweep -> the dofmap IS the geometry dofmap
+        # (pinned in tests/test_host_model.py); no index grids for the 6.7e7-cell slabs of config 5
+        sh = mesh.shape
+        lshape = (sh[0] + 1, sh[1] + 1) if mesh.topology.dim == 2 else (sh[0] + 1, sh[1] + 1, sh[2] + 1)
+        return mesh.geometry.dofmap, int(np.prod(lshape)), lshape
     if mesh.topology.dim == 2:
         nx, ny = mesh.shape
         ly = k * ny + 1

@@ -114,16 +114,18 @@ def create_box(points, n, cell_type=CellType.hexahedron, dtype=np.float64) -> Me
     zs = p[0, 2] + (p[1, 2] - p[0, 2]) * (np.arange(nz + 1) / nz)
     nvx, nvy = nx + 1, ny + 1
     x = np.empty((nvx * nvy * (nz + 1), 3), dtype=dtype)
-    x[:, 0] = np.tile(xs, nvy * (nz + 1))  # vertex id = (iz*nvy + iy)*nvx + ix  (x fastest)
-    x[:, 1] = np.tile(np.repeat(ys, nvx), nz + 1)
-    x[:, 2] = np.repeat(zs, nvx * nvy)
-    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-    v0 = ((iz * nvy + iy) * nvx + ix).reshape(-1)  # cell id = (iz*ny + iy)*nx + ix
+    xv = x.reshape(nz + 1, nvy, nvx, 3)  # vertex id = (iz*nvy + iy)*nvx + ix  (x fastest); filled by broadcasting
+    xv[..., 0] = xs[None, None, :]
+    xv[..., 1] = ys[None, :, None]
+    xv[..., 2] = zs[:, None, None]
+    assert nvx * nvy * (nz + 1) < 2**31, "vertex count exceeds int32 (the reference's geometry dofmap is int32)"
+    # cell id = (iz*ny + iy)*nx + ix; first vertex by broadcasting (no index grids: config 5 slabs have 6.7e7 cells)
+    v0 = ((np.arange(nz, dtype=np.int32) * nvy)[:, None, None] + np.arange(ny, dtype=np.int32)[None, :, None]) * np.int32(nvx) + np.arange(nx, dtype=np.int32)[None, None, :]
+    v0 = v0.reshape(-1)
     sy, sz = nvx, nvx * nvy
-    cells = np.stack(
-        [v0, v0 + 1, v0 + sy, v0 + sy + 1, v0 + sz, v0 + sz + 1, v0 + sz + sy, v0 + sz + sy + 1],
-        axis=1,
-    ).astype(np.int32)
+    cells = np.empty((nx * ny * nz, 8), dtype=np.int32)
+    for k, off in enumerate([0, 1, sy, sy + 1, sz, sz + 1, sz + sy, sz + sy + 1]):
+        cells[:, k] = v0 + np.int32(off)
     return Mesh(
         Geometry(x, 3, cells),
         Topology(3, CellType.hexahedron, nx * ny * nz),

@@ -59,28 +59,55 @@ def build_pattern(dofmap: np.ndarray, num_dofs: int, bs: int = 1, cells=None) ->
     return Pattern(indptr, np.ascontiguousarray(cols, dtype=np.int32), num_dofs * bs)
 
 
-def build_pattern_torch(dofmap, num_dofs: int, bs: int = 1, chunk_cells: int = 1 << 22):
+def build_pattern_torch(dofmap, num_dofs: int, bs: int = 1, chunk_pairs: int = 1 << 28):
     """Device builder (torch tensors in, torch tensors out: indptr int64, indices int32).
-    Same algorithm; pairs are generated and de-duplicated in chunks of cells to bound memory."""
+
+    Row-chunked: the (dof, cell) incidences are sorted by dof once; a chunk of consecutive rows then owns a
+    contiguous slice of that list, its candidate columns are the dofs of the incident cells, and de-duplicating
+    them gives the FINAL rows of the chunk -- nothing is merged across chunks, so the peak memory is a few
+    ``chunk_pairs`` keys whatever the mesh size (config 5: 6.7e7 hexahedra per GPU, 1.8e9 nonzeros)."""
     import torch
 
-    d = dofmap.to(torch.int64)
-    uniq = None
-    for s in range(0, d.shape[0], chunk_cells):
-        dc = d[s : s + chunk_cells]
-        k = torch.unique((dc[:, :, None] * num_dofs + dc[:, None, :]).reshape(-1))
-        uniq = k if uniq is None else torch.unique(torch.cat([uniq, k]))
-    rows = torch.div(uniq, num_dofs, rounding_mode="floor")
-    cols = (uniq - rows * num_dofs).to(torch.int32)
-    indptr = torch.zeros(num_dofs + 1, dtype=torch.int64, device=d.device)
-    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=num_dofs), 0)
+    dev = dofmap.device
+    C, n = dofmap.shape
+    d = dofmap.reshape(-1).to(torch.int64)
+    order = torch.argsort(d, stable=True)           # incidences sorted by dof; order // n = cell
+    inc_cell = torch.div(order, n, rounding_mode="floor")
+    per_row = torch.bincount(d, minlength=num_dofs)  # incident cells per row
+    del d, order
+    inc_ptr = torch.zeros(num_dofs + 1, dtype=torch.int64, device=dev)
+    inc_ptr[1:] = torch.cumsum(per_row, 0)
+    # row chunks holding at most ~chunk_pairs candidate (row, col) pairs
+    cand_ptr = (inc_ptr * n).cpu().numpy()
+    bounds = [0]
+    while bounds[-1] < num_dofs:
+        r1 = int(np.searchsorted(cand_ptr, cand_ptr[bounds[-1]] + chunk_pairs, side="right")) - 1
+        bounds.append(min(num_dofs, max(r1, bounds[-1] + 1)))
+    dm = dofmap.to(torch.int64)
+    counts = torch.zeros(num_dofs, dtype=torch.int64, device=dev)
+    cols_parts = []
+    for r0, r1 in zip(bounds[:-1], bounds[1:]):
+        i0, i1 = int(inc_ptr[r0]), int(inc_ptr[r1])
+        if i1 == i0:
+            continue
+        rows = torch.repeat_interleave(torch.arange(r0, r1, device=dev), per_row[r0:r1])  # row of every incidence
+        keys = (rows[:, None] * num_dofs + dm[inc_cell[i0:i1]]).reshape(-1)
+        keys = torch.unique(keys)
+        rr = torch.div(keys, num_dofs, rounding_mode="floor")
+        counts[r0:r1] = torch.bincount(rr - r0, minlength=r1 - r0)
+        cols_parts.append((keys - rr * num_dofs).to(torch.int32))
+        del rows, keys, rr
+    cols = torch.cat(cols_parts) if cols_parts else torch.zeros(0, dtype=torch.int32, device=dev)
+    del cols_parts
+    indptr = torch.zeros(num_dofs + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(counts, 0)
     if bs > 1:
         m = indptr[1:] - indptr[:-1]
-        E = (cols.to(torch.int64)[:, None] * bs + torch.arange(bs, device=d.device)[None, :]).reshape(-1)
+        E = (cols.to(torch.int64)[:, None] * bs + torch.arange(bs, device=dev)[None, :]).reshape(-1)
         len_exp = torch.repeat_interleave(m * bs, bs)
-        indptr_exp = torch.zeros(len_exp.shape[0] + 1, dtype=torch.int64, device=d.device)
+        indptr_exp = torch.zeros(len_exp.shape[0] + 1, dtype=torch.int64, device=dev)
         indptr_exp[1:] = torch.cumsum(len_exp, 0)
         start = torch.repeat_interleave(indptr[:-1] * bs, bs)
-        src = torch.repeat_interleave(start - indptr_exp[:-1], len_exp) + torch.arange(int(indptr_exp[-1]), device=d.device)
+        src = torch.repeat_interleave(start - indptr_exp[:-1], len_exp) + torch.arange(int(indptr_exp[-1]), device=dev)
         indptr, cols = indptr_exp, E[src].to(torch.int32)
     return indptr, cols.contiguous()

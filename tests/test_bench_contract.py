@@ -9,7 +9,9 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    env = dict(os.environ, CQ_BENCH_SAMPLE_COLS="8")  # 8 x 2048 cells per step instead of 192 x 2048
+    # 8 x 2048 cells per step instead of 192 x 2048; OMP_NUM_THREADS=1 is what torch.distributed.run exports at N > 1:
+    # the arm must still use every core (round 1's N > 1 reference lines ran on one thread)
+    env = dict(os.environ, CQ_BENCH_SAMPLE_COLS="8", OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env, timeout=600)  # fmt: skip
     assert r.returncode == 0, r.stderr[-2000:]
@@ -18,7 +20,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "element_tensors_per_s" and d["unit"] == "element tensors/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -309,7 +309,7 @@ def test_pattern_builders_agree(cuda_backend):
         mesh = make_mesh(tdim, False)
         V = cq.FunctionSpace(mesh, ("Lagrange", degree), bs) if bs > 1 else cq.FunctionSpace(mesh, ("Lagrange", degree))
         p = build_pattern(V.dofmap.list, V.dofmap.num_dofs, bs)
-        ip, ix = build_pattern_torch(torch.from_numpy(V.dofmap.list).cuda(), V.dofmap.num_dofs, bs, chunk_cells=7)
+        ip, ix = build_pattern_torch(torch.from_numpy(V.dofmap.list).cuda(), V.dofmap.num_dofs, bs, chunk_pairs=200)
         assert np.array_equal(ip.cpu().numpy(), p.indptr) and np.array_equal(ix.cpu().numpy(), p.indices)
 
 

@@ -134,3 +134,46 @@ def test_no_cpu_fallback_without_gpu():
     V = cq.FunctionSpace(m, ("Lagrange", 1))
     with pytest.raises(RuntimeError):
         cq.assemble_matrix(forms.mass(V), [([0], [np.full(2, 0.5)], [np.ones(1)])])
+
+
+def test_degree1_dofmap_is_the_geometry_dofmap_and_box_mesh_matches_index_grids():
+    """The degree-1 shortcut of fem._build_dofmap and the broadcast construction of create_box (no index grids)."""
+    import customquad_b200 as cq
+    from customquad_b200.fem import reference_lattice
+
+    for mesh in (cq.create_rectangle([[0, 0], [1, 2]], [3, 5]), cq.create_box([[0, 0, 0], [1, 2, 3]], [3, 4, 2])):
+        V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+        assert np.array_equal(V.dofmap.list, mesh.geometry.dofmap)
+        # independent statement: dof of local vertex v of cell (ix, iy[, iz]) by lattice position
+        r = reference_lattice(mesh.cell_type, 1)
+        if mesh.topology.dim == 2:
+            nx, ny = mesh.shape
+            for ix in range(nx):
+                for iy in range(ny):
+                    want = [(ix + r[v, 1]) * (ny + 1) + iy + r[v, 0] for v in range(4)]
+                    assert list(V.dofmap.list[ix * ny + iy]) == want
+        else:
+            nx, ny, nz = mesh.shape
+            for iz in range(nz):
+                for iy in range(ny):
+                    for ix in range(nx):
+                        c = (iz * ny + iy) * nx + ix
+                        want = [((iz + r[v, 2]) * (ny + 1) + iy + r[v, 1]) * (nx + 1) + ix + r[v, 0] for v in range(8)]
+                        assert list(V.dofmap.list[c]) == want
+                        x0 = mesh.geometry.x[mesh.geometry.dofmap[c, 0]]
+                        assert np.allclose(x0, [ix / nx, 2 * iy / ny, 3 * iz / nz])
+
+
+def test_row_chunked_torch_pattern_builder_on_cpu_tensors():
+    import torch
+
+    import customquad_b200 as cq
+    from customquad_b200.sparsity import build_pattern, build_pattern_torch
+
+    for mesh, degree, bs in ((cq.create_rectangle([[0, 0], [1, 1]], [6, 5]), 2, 2), (cq.create_box([[0, 0, 0], [1, 1, 1]], [3, 4, 2]), 1, 1),
+                             (cq.create_box([[0, 0, 0], [1, 1, 1]], [2, 2, 3]), 2, 3)):
+        V = cq.FunctionSpace(mesh, ("Lagrange", degree), bs)
+        p = build_pattern(V.dofmap.list, V.dofmap.num_dofs, bs)
+        for chunk in (50, 1000, 1 << 28):
+            ip, ix = build_pattern_torch(torch.from_numpy(np.ascontiguousarray(V.dofmap.list)), V.dofmap.num_dofs, bs, chunk_pairs=chunk)
+            assert np.array_equal(ip.numpy(), p.indptr) and np.array_equal(ix.numpy(), p.indices)
