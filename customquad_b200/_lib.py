@@ -28,7 +28,8 @@ class SpaceDesc(C.Structure):
 
 class QuadratureDesc(C.Structure):
     _fields_ = [("num_entries", C.c_int64), ("num_points", C.c_int64), ("cells", C.c_void_p), ("offsets", C.c_void_p),
-                ("pts", C.c_void_p), ("weights", C.c_void_p), ("normals", C.c_void_p)]  # fmt: skip
+                ("pts", C.c_void_p), ("weights", C.c_void_p), ("normals", C.c_void_p),
+                ("plane_entries", C.c_int64), ("plane_tiles", C.c_int32), ("pad_", C.c_int32)]  # fmt: skip
 
 
 class CsrDesc(C.Structure):
@@ -83,6 +84,8 @@ _SIGNATURES = {
     "cq_mesh_classify": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(MeshDesc), C.POINTER(C.c_int32), C.c_void_p]),
     "cq_scatter_map_stride": (C.c_int, [C.c_int, C.c_int]),
     "cq_build_scatter_map": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(CsrDesc), C.c_void_p, C.c_void_p]),
+    "cq_csr_expand_blocks": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cq_assemble_ghost_penalty": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.c_int64, C.c_void_p, C.POINTER(CsrDesc), C.c_void_p]),
     "cq_tabulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cq_element_tensors": (C.c_int, [C.c_void_p, C.POINTER(FormDesc), C.POINTER(MeshDesc), C.POINTER(SpaceDesc), C.POINTER(QuadratureDesc), C.c_void_p, C.c_void_p]),
     "cq_csr_accumulate_rows": (C.c_int, [C.c_void_p, C.POINTER(CsrDesc), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -6,6 +6,7 @@ MatSetValuesLocal replaced by one CUDA launch per cell integral through the C-AB
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -75,26 +76,34 @@ def pattern_on_device(V, dev, cells=None):
     return V._dev[key]
 
 
-def scatter_map_on_device(V, dev, indptr, indices):
+def scatter_map_on_device(V, dev, A):
     """cq_build_scatter_map: per-cell positions of the element tensor entries inside their CSR
     rows, built once per (space, pattern) -- the stand-in for the local-to-global mapping and
     preallocation a PETSc Mat carries.  Returns None when a row is too long for the uint8 map
-    (the kernels then search the rows like MatSetValuesLocal does)."""
+    (the kernels then search the rows like MatSetValuesLocal does).
+
+    The map of the form's full pattern is shared by every matrix of the space (cached on the space, next to the
+    pattern); a matrix on its own pattern (facet couplings) keeps its map itself, so that a map can never outlive
+    the pattern tensors it was built for."""
     torch = _torch()
-    key = ("scatter_map", dev, indptr.data_ptr())
-    if key not in V._dev:
+    shared = V._dev.get(("pattern", dev, None))
+    if shared is not None and shared[0] is A.indptr:
+        cache, key = V._dev, ("scatter_map", dev)
+    else:
+        cache, key = A.__dict__.setdefault("_cache", {}), ("scatter_map", dev, id(V))
+    if key not in cache:
         L = _lib.load()
         stride = L.cq_scatter_map_stride(int(V.mesh.cell_type), int(V.degree))
         dm = space_on_device(V, dev)
         out = torch.empty((dm.shape[0], stride), dtype=torch.uint8, device=dev)
-        A = _lib.CsrDesc(V.num_dofs, int(indices.shape[0]), _ptr(indptr), _ptr(indices), None)
-        rc = L.cq_build_scatter_map(_lib.ctx(dev.index), int(V.mesh.cell_type), int(V.degree), int(V.bs), dm.shape[0], _ptr(dm), C.byref(A), _ptr(out), _stream_ptr())
+        desc = _lib.CsrDesc(V.num_dofs, int(A.indices.shape[0]), _ptr(A.indptr), _ptr(A.indices), None)
+        rc = L.cq_build_scatter_map(_lib.ctx(dev.index), int(V.mesh.cell_type), int(V.degree), int(V.bs), dm.shape[0], _ptr(dm), C.byref(desc), _ptr(out), _stream_ptr())
         if rc == -3:  # CQ_ERR_UNSUPPORTED: rows longer than 255
             out = None
         else:
             _lib.check(rc)
-        V._dev[key] = out
-    return V._dev[key]
+        cache[key] = out
+    return cache[key]
 
 
 def coefficient_on_device(f, dev):
@@ -118,6 +127,33 @@ def qr_on_device(q: RaggedQuadrature, dev):
         up = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
         q._dev[dev] = (up(q.cells), up(q.offsets), up(q.pts), up(q.w), up(q.n))
     return q._dev[dev]
+
+
+L2_TILE_BYTES = int(os.environ.get("CQ_L2_TILE_BYTES", 24 << 20))  # matrix rows one traversal tile may keep live between two cell layers (B200 L2: 126 MB, shared with the rule stream)
+
+
+def _traversal_hint(mesh, q, cells_dev, A):
+    """cq_quadrature.plane_entries / plane_tiles for a matrix assembly over a structured hexahedral mesh whose rule lists
+    whole cell layers in order (cells c0, c0 + 1, ... with c0 at the start of a layer): when the rows of the dof planes
+    one cell layer scatters into do not fit the L2, walk the list tile by tile (include/cq_b200.h).  (0, 0) otherwise."""
+    if A is None or mesh.topology.dim != 3 or len(getattr(mesh, "shape", ())) != 3 or q.num_entries == 0:
+        return 0, 0
+    per_layer = int(mesh.shape[0]) * int(mesh.shape[1])
+    if q.num_entries < 2 * per_layer:
+        return 0, 0
+    key = ("layers", per_layer)
+    if key not in q._dev:  # once per rule: consecutive cells starting at a layer boundary?
+        c0 = int(cells_dev[0])
+        ok = c0 % per_layer == 0 and int(cells_dev[-1]) - c0 + 1 == q.num_entries and bool((cells_dev[1:] - cells_dev[:-1] == 1).all())
+        q._dev[key] = ok
+    if not q._dev[key]:
+        return 0, 0
+    dof_planes = A.shape[0] / max(1, int(mesh.shape[2]))  # rows per cell layer (k dof planes, + 1 shared)
+    live = 8.0 * A.nnz / A.shape[0] * dof_planes * 2.0    # bytes of matrix rows one cell layer touches, roughly
+    tiles = int(np.ceil(live / L2_TILE_BYTES))
+    if tiles <= 1:
+        return 0, 0
+    return per_layer, min(tiles, max(1, int(mesh.shape[1]) // 2))  # at least two cell rows per tile
 
 
 # ---- descriptors --------------------------------------------------------------------------------
@@ -144,7 +180,7 @@ class _Call:
             dm = space_on_device(self.V, dev)
             co = coefficient_on_device(form.coefficient, dev) if form.coefficient is not None else None
             # the map belongs to the full-form pattern; matrices on a "cells" pattern search their rows
-            pos = scatter_map_on_device(self.V, dev, A.indptr, A.indices) if (A is not None and A.full_pattern) else None
+            pos = scatter_map_on_device(self.V, dev, A) if (A is not None and A.full_pattern) else None
             self.keep += [dm, co, pos]
             self.space = _lib.SpaceDesc(self.V.dofmap.num_dofs, _ptr(dm), _ptr(co), _ptr(pos))
         consts = form.consts()
@@ -159,7 +195,8 @@ class _Call:
         else:
             t = qr_on_device(q, dev)
             self.keep += list(t)
-            self.qr = _lib.QuadratureDesc(q.num_entries, q.num_points, *[_ptr(a) for a in t])
+            pe, pt = _traversal_hint(mesh, q, t[0], A)
+            self.qr = _lib.QuadratureDesc(q.num_entries, q.num_points, *[_ptr(a) for a in t], pe, pt, 0)
 
     def space_ref(self):
         return None if self.space is None else C.byref(self.space)
@@ -171,17 +208,43 @@ def set_fused_zero(on: bool) -> None:
     _lib.check(_lib.load().cq_ctx_set_fused_zero(_lib.ctx(_dev().index), int(bool(on))))
 
 
-def create_matrix(form: Form, pattern_cells=None, zero: bool = True) -> CSRMatrix:
+def create_matrix(form: Form, pattern_cells=None, zero: bool = True, facets=None) -> CSRMatrix:
     """Zeroed matrix on the form's pattern (create_matrix + zeroEntries, assemble_matrix.py:19-20).
-    ``zero=False`` leaves the values uninitialised for ``assemble_matrix(..., zero=True)``."""
+    ``zero=False`` leaves the values uninitialised for ``assemble_matrix(..., zero=True)``.
+    ``facets`` [nf, 3] (low cell, high cell, axis; cutfem.ghost_penalty_facets): also the couplings across these
+    interior facets, as dolfinx's create_matrix adds them for a form with a dS integral (demo/poisson.py:168-170)."""
     torch = _torch()
     dev = _dev()
     V = form.function_spaces[0]
     indptr, indices = pattern_on_device(V, dev, pattern_cells)
+    if facets is not None and len(facets):
+        from .sparsity import add_macro_couplings
+
+        f = np.asarray(facets, dtype=np.int64)
+        macro = np.concatenate([V.dofmap.list[f[:, 0]], V.dofmap.list[f[:, 1]]], axis=1)
+        indptr, indices = add_macro_couplings(indptr, indices, V.dofmap.num_dofs, V.bs, macro)
     data = (torch.zeros if zero else torch.empty)(indices.shape[0], dtype=torch.float64, device=dev)
     n = V.num_dofs
     A = CSRMatrix(indptr, indices, data, (n, n), dev.index, _stream_ptr())
     A.full_pattern = pattern_cells is None
+    return A
+
+
+def assemble_ghost_penalty(V, facets, betas: float, A: CSRMatrix) -> CSRMatrix:
+    """A += betas * avg(h) * inner(jump(n, grad u), jump(n, grad v)) * dS over ``facets`` (cq_assemble_ghost_penalty;
+    demo/poisson.py:160,168-170, which the reference assembles with dolfinx).  ``A`` must come from
+    ``create_matrix(form, facets=facets)``.  Axis-aligned meshes, degree 1 or 2, any block size."""
+    torch = _torch()
+    dev = _dev()
+    gd, xc, mflags = mesh_on_device(V.mesh, dev)
+    md = _lib.MeshDesc(V.mesh.num_cells, V.mesh.geometry.x.shape[0], _ptr(gd), _ptr(xc), mflags)
+    dm = space_on_device(V, dev)
+    sd = _lib.SpaceDesc(V.dofmap.num_dofs, _ptr(dm), None, None)
+    f = torch.as_tensor(np.ascontiguousarray(facets, dtype=np.int32), device=dev)
+    csr = _csr_desc(A)
+    _lib.check(_lib.load().cq_assemble_ghost_penalty(_lib.ctx(dev.index), int(V.mesh.cell_type), int(V.degree), int(V.bs), float(betas), C.byref(md), C.byref(sd),
+                                                     int(f.shape[0]), _ptr(f), C.byref(csr), _stream_ptr()))  # fmt: skip
+    A.assembled = False
     return A
 
 

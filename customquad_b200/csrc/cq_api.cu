@@ -92,6 +92,11 @@ static int pack(cq_ctx* ctx, const cq_form_desc* f, const cq_mesh* mesh, const c
   P.work_counter = ctx->work_counter;
   P.mesh_flags = mesh->flags;
   P.num_points = qr->num_points;
+  if (qr->plane_entries >= 64 && qr->plane_tiles > 1 && qr->num_entries > qr->plane_entries) {
+    P.tile_sp = qr->plane_entries / 32;
+    P.tile_sg = (P.tile_sp + qr->plane_tiles - 1) / qr->plane_tiles;
+    if (P.tile_sg < 1) P.tile_sg = 1;
+  }
   P.bs = f->bs;
   for (int i = 0; i < f->nconsts; ++i) P.p[i] = f->consts[i];
   P.betaN = nitsche ? (f->nconsts > 0 ? f->consts[0] : 0.0) : 0.0;
@@ -192,6 +197,82 @@ __global__ void scatter_map_kernel(const int32_t* __restrict__ dofmap, int64_t n
     const int64_t rel = s < 0 ? -1 : (s - indptr[row]) / bs;
     if (s < 0 || rel > 255 || (s - indptr[row]) % bs != 0) atomicExch(err, s < 0 ? 1 : 2);
     out[c * stride + ij] = (uint8_t)(rel < 0 ? 0 : rel);
+  }
+}
+
+// blocked row r*bs + a: columns c*bs + b of the scalar row r; one warp per scalar row
+__global__ void expand_blocks_kernel(const int64_t num_rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int bs,
+                                     int64_t* __restrict__ indptr_out, int32_t* __restrict__ indices_out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < num_rows; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t s = indptr[r], len = indptr[r + 1] - s;
+    const int64_t base = s * bs * bs, blen = len * bs;  // blocked rows of r start at base, base + blen, ...
+    if (lane < bs) indptr_out[r * bs + lane] = base + lane * blen;
+    if (r == num_rows - 1 && lane == 0) indptr_out[num_rows * bs] = base + bs * blen;
+    for (int64_t i = lane; i < blen; i += 32) {
+      const int32_t col = indices[s + i / bs] * bs + (int32_t)(i % bs);
+      for (int a = 0; a < bs; ++a) indices_out[base + a * blen + i] = col;
+    }
+  }
+}
+
+// Ghost penalty on axis-aligned cells: one thread per (facet, i, j), i, j in the 2N dofs of the two cells.
+//   M_ij = betas * avg(h) * |F| * sum_q gw_q J_i(q) J_j(q),  J = (d_ax psi^lo / J_ax^lo, -d_ax psi^hi / J_ax^hi) at the facet points
+// (tensor Gauss rule with DEG + 1 points per facet direction: exact, the integrand has degree 2 DEG per direction).
+template <int DIM, int DEG>
+__global__ void ghost_penalty_kernel(const KParams P, const int64_t num_facets, const int32_t* __restrict__ facets, const double betas) {
+  constexpr int N = Lattice<DIM, DEG>::N, N2 = 2 * N, NG = DEG + 1, NQ = DIM == 2 ? NG : NG * NG;
+  const double g2[2] = {0.21132486540518713, 0.7886751345948129}, w2[2] = {0.5, 0.5};
+  const double g3[3] = {0.1127016653792583, 0.5, 0.8872983346207417}, w3[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  const int64_t total = num_facets * N2 * N2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = t / (N2 * N2);
+    const int ij = (int)(t - f * N2 * N2), i = ij / N2, j = ij - i * N2;
+    const int32_t cell[2] = {facets[3 * f], facets[3 * f + 1]};
+    const int ax = facets[3 * f + 2];
+    double Jax[2], hK[2], area = 1.0;
+    for (int s = 0; s < 2; ++s) {
+      double X[1 << DIM][DIM];
+      load_cell_vertices<DIM>(P, cell[s], X);
+      CellGeom<DIM> geo;
+      geo.init(X, true);
+      hK[s] = geo.hK;
+      Jax[s] = geo.c[1 << ax][ax];
+      if (s == 0)
+        for (int d = 0; d < DIM; ++d)
+          if (d != ax) area *= fabs(geo.c[1 << d][d]);
+    }
+    double m = 0.0;
+    for (int q = 0; q < NQ; ++q) {
+      // facet point: Gauss coordinates in the directions != ax; xi_ax = 1 in the low cell, 0 in the high cell
+      double gw = 1.0, xi[2][DIM];
+      int qq = q;
+      for (int d = 0; d < DIM; ++d) {
+        if (d == ax) { xi[0][d] = 1.0; xi[1][d] = 0.0; continue; }
+        const int k = qq % NG;
+        qq /= NG;
+        const double gp = DEG == 1 ? g2[k] : g3[k];
+        gw *= DEG == 1 ? w2[k] : w3[k];
+        xi[0][d] = xi[1][d] = gp;
+      }
+      double Ji = 0.0, Jj = 0.0;
+      for (int s = 0; s < 2; ++s) {
+        double psi[N], gr[N][DIM];
+        tabulate_point<DIM, DEG, false, true>(xi[s], psi, gr);
+        const double sgn = (s == 0 ? 1.0 : -1.0) / Jax[s];
+        for (int k = 0; k < N; ++k) {
+          double v = 0.0;
+          for (int d = 0; d < DIM; ++d) v = d == ax ? gr[k][d] : v;
+          if (i == s * N + k) Ji = sgn * v;
+          if (j == s * N + k) Jj = sgn * v;
+        }
+      }
+      m = fma(gw * Ji, Jj, m);
+    }
+    m *= betas * 0.5 * (hK[0] + hK[1]) * area;
+    const int32_t di = __ldg(P.dofmap + (int64_t)cell[i / N] * N + (i % N));
+    const int32_t dj = __ldg(P.dofmap + (int64_t)cell[j / N] * N + (j % N));
+    for (int a = 0; a < P.bs; ++a) csr_add(P, (int64_t)di * P.bs + a, dj * P.bs + a, m);
   }
 }
 
@@ -465,6 +546,51 @@ int cq_build_scatter_map(cq_ctx* ctx, int cell_type, int degree, int bs, int64_t
   return CQ_OK;
 }
 
+int cq_csr_expand_blocks(cq_ctx* ctx, int64_t num_rows, const int64_t* indptr, const int32_t* indices, int bs, int64_t* indptr_out,
+                         int32_t* indices_out, void* stream) {
+  if (!ctx || num_rows < 0 || !indptr || !indptr_out || bs < 1 || bs > 3) { set_error("bad argument"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (num_rows == 0) return check_cuda(cudaMemsetAsync(indptr_out, 0, sizeof(int64_t), s), "memset");
+  if (!indices || !indices_out) { set_error("indices null"); return CQ_ERR_INVALID; }
+  const int64_t blocks = (num_rows + 7) / 8 < (int64_t)ctx->num_sms * 16 ? (num_rows + 7) / 8 : (int64_t)ctx->num_sms * 16;
+  expand_blocks_kernel<<<(int)blocks, 256, 0, s>>>(num_rows, indptr, indices, bs, indptr_out, indices_out);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "expand_blocks_kernel launch");
+}
+
+int cq_assemble_ghost_penalty(cq_ctx* ctx, int cell_type, int degree, int bs, double betas, const cq_mesh* mesh, const cq_space* space,
+                              int64_t num_facets, const int32_t* facets, const cq_csr* A, void* stream) {
+  if (!ctx || !mesh || !space || !space->dofmap || !mesh->geom_dofmap || !mesh->coords || !A || !A->indptr || !A->indices || !A->values || num_facets < 0) {
+    set_error("null argument");
+    return CQ_ERR_INVALID;
+  }
+  if ((cell_type != CQ_CELL_QUADRILATERAL && cell_type != CQ_CELL_HEXAHEDRON) || (degree != 1 && degree != 2) || bs < 1 || bs > 3) {
+    set_error("ghost penalty: quadrilaterals / hexahedra, degree 1 or 2, bs 1..3");
+    return CQ_ERR_UNSUPPORTED;
+  }
+  if (!(mesh->flags & CQ_MESH_AXIS_ALIGNED)) { set_error("ghost penalty: axis-aligned cells only (cq_mesh.flags)"); return CQ_ERR_UNSUPPORTED; }
+  if (num_facets == 0) return CQ_OK;
+  if (!facets) { set_error("facets null"); return CQ_ERR_INVALID; }
+  if (int rc = set_device(ctx)) return rc;
+  KParams P;
+  memset(&P, 0, sizeof P);
+  P.geom_dofmap = mesh->geom_dofmap; P.coords = mesh->coords; P.dofmap = space->dofmap;
+  P.indptr = A->indptr; P.indices = A->indices; P.values = A->values; P.err_flag = ctx->err_flag; P.bs = bs;
+  int n = degree + 1;
+  n = cell_type == CQ_CELL_QUADRILATERAL ? n * n : n * n * n;
+  const int64_t total = num_facets * 4 * n * n;
+  const int grid = (int)((total + 127) / 128 < (int64_t)ctx->num_sms * 16 ? (total + 127) / 128 : (int64_t)ctx->num_sms * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool quad = cell_type == CQ_CELL_QUADRILATERAL;
+  if (quad && degree == 1) ghost_penalty_kernel<2, 1><<<grid, 128, 0, s>>>(P, num_facets, facets, betas);
+  else if (quad) ghost_penalty_kernel<2, 2><<<grid, 128, 0, s>>>(P, num_facets, facets, betas);
+  else if (degree == 1) ghost_penalty_kernel<3, 1><<<grid, 128, 0, s>>>(P, num_facets, facets, betas);
+  else ghost_penalty_kernel<3, 2><<<grid, 128, 0, s>>>(P, num_facets, facets, betas);
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "ghost_penalty_kernel launch");
+}
+
 int cq_tabulate(cq_ctx* ctx, int cell_type, int degree, int basix_derivative, int64_t num_points, const double* pts,
                 double* out, void* stream) {
   if (!ctx || (num_points > 0 && (!pts || !out))) { set_error("null argument"); return CQ_ERR_INVALID; }
@@ -720,6 +846,8 @@ static int run_host_chunked(cq_ctx* ctx, const int cell_type, const cq_quadratur
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(s, ctx->ev[c], 0), "cudaStreamWaitEvent");
     if (rc) return rc;
     cq_quadrature qc = qd;
+    qc.plane_entries = 0;  // a chunk is a sub-list: no traversal hint
+    qc.plane_tiles = 0;
     qc.cells = qd.cells + k0;
     qc.offsets = qd.offsets + k0;
     qc.num_entries = k1 - k0;

@@ -33,8 +33,10 @@ struct KParams {
   double* out;     // vector b / scalar m / element tensors
   int* err_flag;
   const uint8_t* __restrict__ elem_pos;  // scatter positions [num_cells, NPOS] or null
-  unsigned int* work_counter;            // ctx-owned, zeroed before a staged launch
+  unsigned int* work_counter;            // ctx-owned ticket counter of the staged kernels, zeroed before a launch with `dynamic`
+  int dynamic;                           // 1: producers draw their stages from work_counter (in traversal order) instead of the static interleaving
   int64_t num_points;                    // length of pts / w (bulk-copy tail handling)
+  long long tile_sp, tile_sg;            // traversal hint (cq_quadrature.plane_entries / plane_tiles) in stages: per plane, per tile; 0 = list order
   int stage_points;                      // points capacity of one smem stage
   int mesh_flags;                        // cq_mesh.flags
   int dbg;                               // profiling builds only (-DCQ_PROFILING, CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
@@ -98,6 +100,26 @@ CQ_DEVINL void csr_add(const KParams& P, const int64_t row, const int32_t col, c
   const int64_t s = csr_find(P.indptr, P.indices, row, col);
   if (s >= 0) red_add_f64(P.values + s, v);
   else atomicExch(P.err_flag, 1);
+}
+
+// Traversal position -> stage index (32 consecutive list entries) under the plane / tile hint: the NS stages form
+// planes of SP stages (the last one possibly partial); tile g holds the stages [g SG, (g+1) SG) of every plane; the
+// traversal runs tile by tile, inside a tile plane by plane.  A bijection of [0, NS); identity without the hint.
+CQ_DEVINL long long stage_of(const KParams& P, long long tp, const long long NS) {
+  const long long SP = P.tile_sp, SG = P.tile_sg;
+  if (SP <= 0) return tp;
+  const long long NPf = NS / SP, L = NS - NPf * SP;
+  for (long long g0 = 0;; g0 += SG) {
+    const long long len = SG < SP - g0 ? SG : SP - g0;                       // stages of this tile inside a full plane
+    const long long endL = L < g0 + len ? L : g0 + len;
+    const long long lenL = endL > g0 ? endL - g0 : 0;                        // ... inside the partial last plane
+    const long long cnt = NPf * len + lenL;
+    if (tp < cnt || g0 + SG >= SP) {
+      const long long p = tp < NPf * len ? tp / len : NPf;
+      return p * SP + g0 + (tp - p * len);
+    }
+    tp -= cnt;
+  }
 }
 
 // upper-triangular entry index -> (i, j)

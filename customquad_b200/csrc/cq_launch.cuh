@@ -36,6 +36,7 @@ static int ensure_smem_optin(cq_ctx* ctx, const void* kernel, size_t smem) {
 // Sets P.zero_hi / zero_done / zero_ahead for a launch of `grid` CTAs (stream-ordered).  The caller has checked that
 // the kernel supports it; on return P.zero_req is cleared.
 static int prepare_fused_zero(cq_ctx* ctx, KParams& P, const int n, const int grid, cudaStream_t s) {
+  P.tile_sp = P.tile_sg = 0;  // the zeroing front follows the list order
   const int64_t num_stages = (P.num_entries + 31) / 32;
   const int64_t waves = (num_stages + grid - 1) / grid;
   if ((size_t)waves > ctx->zero_waves) {
@@ -60,6 +61,18 @@ static int prepare_fused_zero(cq_ctx* ctx, KParams& P, const int n, const int gr
   P.zero_ahead = ahead < 4 ? 4 : ahead;  // at least the batch of the zeroing warp (no deadlock: cq_staged_kernel.cuh)
   P.zero_req = 0;
   return CQ_OK;
+}
+
+// Stage distribution of a persistent launch: dynamic tickets for long lists (more than CQ_DYNAMIC_ROUNDS rounds of
+// grid * slots stages; see staged_producer), the static interleaving otherwise (one dependent round trip less per stage).
+#ifndef CQ_DYNAMIC_ROUNDS
+#define CQ_DYNAMIC_ROUNDS 512
+#endif
+static int choose_dynamic(cq_ctx* ctx, KParams& P, const int64_t num_stages, const int64_t per_round, cudaStream_t s) {
+  const int mode = CQ_TUNE_INT("CQ_DYNAMIC", -1);  // profiling builds: 0 / 1 force
+  P.dynamic = mode >= 0 ? mode : (num_stages > (int64_t)CQ_DYNAMIC_ROUNDS * per_round ? 1 : 0);
+  if (!P.dynamic) return CQ_OK;
+  return check_cuda(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int), s), "memset(work_counter)");
 }
 
 // kernels without the fused zeroing: a memset does it
@@ -113,6 +126,7 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   if (int rc = ensure_smem_optin(ctx, (const void*)kernel, smem)) return rc;
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
+  if (int rc = choose_dynamic(ctx, P, num_stages, grid * NPW, s)) return rc;
   kernel<<<grid, (NPW + NCW) * 32, smem, s>>>(P);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
@@ -163,6 +177,8 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
     }
     if (int rc = prezero(P, s)) return rc;
   }
+  if (NPP == 1)
+    if (int rc = choose_dynamic(ctx, P, num_stages, grid * NPW, s)) return rc;
   kernel<<<grid, (NPW * NPP + NMW + NXW + ZW) * 32, smem, s>>>(P);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "assemble_moment_split_kernel launch");

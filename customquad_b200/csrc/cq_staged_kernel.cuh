@@ -69,6 +69,15 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
     int64_t next_t = ((int64_t)sub * nslots + slot) * gridDim.x + blockIdx.x;
     const int64_t step_t = round_t * npp;
     int round = sub;
+    // P.dynamic (long lists; npp == 1): the stages come from a global ticket counter instead, drawn one iteration
+    // ahead so that the atomic's round trip hides in the pipeline.  The static interleaving lets the CTAs drift apart
+    // -- nothing ties a fast SM to a slow one, and over the ~2400 rounds of a 6.7e7-cell list (config 5) the drift
+    // reaches many rounds -- so that rows shared by neighbouring cells are long evicted from the L2 when the second
+    // contribution arrives: ncu counted 3.3 DRAM reads and 2.4 writes per matrix line.  With tickets the stages in
+    // flight are always ~grid * slots consecutive ones.
+    const bool dyn = P.dynamic != 0;
+    unsigned int ticket = 0;
+    if (dyn && lane == 0) ticket = atomicAdd(P.work_counter, 1u);
     for (;;) {
       // ---------------- publish stage A ----------------
       if (ra.t == -3) break;  // beyond the end marker (another warp of this slot publishes it)
@@ -292,10 +301,16 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
       }
       long long td = next_t < num_stages ? next_t : (next_t - round_t < num_stages ? -1 : -3);
       next_t += step_t;
+      if (dyn) {
+        const unsigned int tk = __shfl_sync(0xffffffffu, ticket, 0);
+        const bool live = rb.t != -1 && rc.t != -1;  // no ticket after this warp's end marker
+        td = !live ? -3 : ((long long)tk < num_stages ? (long long)tk : -1);
+        if (td >= 0 && lane == 0) ticket = atomicAdd(P.work_counter, 1u);  // the next one, consumed one iteration from now
+      }
       rc.t = td;
       rc.valid = false;
       if (td >= 0) {
-        const int64_t k0 = td * CB;
+        const int64_t k0 = stage_of(P, td, num_stages) * CB;  // td: position in the traversal, see stage_of
         const int nent = (int)((P.num_entries - k0) < CB ? (P.num_entries - k0) : CB);
         rc.nent = nent;
         rc.valid = lane < nent;

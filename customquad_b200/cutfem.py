@@ -5,11 +5,12 @@ right before and right after ``customquad.assemble_*`` with dolfinx / PETSc.
 * ``standard_rule``: the tiled Gauss rule that turns the runtime-quadrature path into dolfinx's
   standard assembly over a cell subset (``a_bulk * dx_uncut(uncut_cell_tag)``,
   demo/poisson.py:168-176; the equivalence the reference's tests check, test/common.py:48-57).
-* ``ghost_penalty_facets`` / ``ghost_penalty_matrix``: ``betas * avg(h) * inner(jump(n, grad(u)),
+* ``ghost_penalty_facets`` / ``ghost_penalty``: ``betas * avg(h) * inner(jump(n, grad(u)),
   jump(n, grad(v))) * dS(ghost_penalty_tag)`` (demo/poisson.py:160,168-170) on the facets
-  ``utils.get_facetags`` tags (utils.py:155-182), for Q1 on axis-aligned tensor meshes.  The
-  reference leaves this term to dolfinx; here it is host numpy (it is off the accelerated path,
-  O(number of cut cells) work).
+  ``utils.get_facetags`` tags (utils.py:155-182), for Q1 / Q2 (any block size) on axis-aligned tensor meshes,
+  added into the device CSR by a CUDA kernel (cq_assemble_ghost_penalty) on a pattern that contains the facet
+  couplings (``assemble.create_matrix(form, facets=...)``).  The reference leaves this term to dolfinx.
+  ``ghost_penalty_matrix`` is the host numpy statement of the same term the kernel is tested against.
 """
 from __future__ import annotations
 
@@ -86,17 +87,28 @@ def ghost_penalty_facets(mesh, cut_cells, outside_cells):
     return np.concatenate(out).astype(np.int64)
 
 
+def ghost_penalty(V, facets, betas, A):
+    """The ghost-penalty term added into the device matrix ``A`` (created with ``assemble.create_matrix(form,
+    facets=facets)``) by the CUDA kernel behind cq_assemble_ghost_penalty: A = Ax + Ac1 + Ac2 + stabilisation stays on
+    the GPU.  Degree 1 or 2, any block size, axis-aligned cells."""
+    from .assemble import assemble_ghost_penalty
+
+    return assemble_ghost_penalty(V, facets, betas, A)
+
+
 def ghost_penalty_matrix(V, facets, betas):
-    """scipy CSR of betas * avg(h) * int_F [n.grad u][n.grad v] dS over `facets` (Q1, bs = 1,
-    axis-aligned cells: h = cell diagonal is the same for both cells)."""
+    """Host numpy version (scipy CSR) for scalar spaces (bs = 1; blocked spaces: kron with the identity) on uniform
+    axis-aligned meshes; kept as the small independent statement the device kernel is tested against
+    (tests/test_gpu_cutfem_poisson.py).
+    betas * avg(h) * int_F [n.grad u][n.grad v] dS over `facets` (h = cell diagonal, the same for both cells)."""
     import scipy.sparse as sp
 
-    assert V.degree == 1 and V.bs == 1, "ghost penalty: Q1 scalar spaces"
+    assert V.bs == 1, "ghost penalty (host): scalar spaces"
     mesh = V.mesh
     tdim = mesh.topology.dim
     h = mesh.h()
     hK = float(np.sqrt(np.sum(h * h)))
-    g, gw = gauss_tensor_rule(tdim - 1, 2)  # exact: the integrand is quadratic per facet coordinate
+    g, gw = gauss_tensor_rule(tdim - 1, 2 * V.degree)  # exact: the integrand has degree 2k per facet coordinate
     n = V.dofmap.list.shape[1]
     rows, cols, vals = [], [], []
     for ax in range(tdim):
@@ -107,8 +119,8 @@ def ghost_penalty_matrix(V, facets, betas):
         # facet points in the unit cell of the low cell (xi_ax = 1) and of the high cell (xi_ax = 0)
         P_lo = np.insert(g, ax, 1.0, axis=1)
         P_hi = np.insert(g, ax, 0.0, axis=1)
-        d_lo = fem.tabulate(mesh.cell_type, 1, P_lo)[1][:, :, ax] / h[ax]  # [nq, n] d/dx_ax psi_j
-        d_hi = fem.tabulate(mesh.cell_type, 1, P_hi)[1][:, :, ax] / h[ax]
+        d_lo = fem.tabulate(mesh.cell_type, V.degree, P_lo)[1][:, :, ax] / h[ax]  # [nq, n] d/dx_ax psi_j
+        d_hi = fem.tabulate(mesh.cell_type, V.degree, P_hi)[1][:, :, ax] / h[ax]
         J = np.concatenate([-d_lo, d_hi], axis=1)  # jump over the 2n local dofs
         M = betas * hK * area * np.einsum("q,qi,qj->ij", gw, J, J)
         dofs = np.concatenate([V.dofmap.list[f[:, 0]], V.dofmap.list[f[:, 1]]], axis=1)  # [nf, 2n]

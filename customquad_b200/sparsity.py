@@ -101,6 +101,18 @@ def build_pattern_torch(dofmap, num_dofs: int, bs: int = 1, chunk_pairs: int = 1
     del cols_parts
     indptr = torch.zeros(num_dofs + 1, dtype=torch.int64, device=dev)
     indptr[1:] = torch.cumsum(counts, 0)
+    if bs > 1 and cols.is_cuda:
+        # one kernel, no temporaries (cq_csr_expand_blocks): config 4 expands 1.08e9 scalar couplings into 9.69e9
+        import ctypes as C
+
+        from . import _lib
+
+        indptr_exp = torch.empty(num_dofs * bs + 1, dtype=torch.int64, device=dev)
+        cols_exp = torch.empty(int(indptr[-1]) * bs * bs, dtype=torch.int32, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(_lib.load().cq_csr_expand_blocks(_lib.ctx(dev.index), num_dofs, p(indptr), p(cols), bs, p(indptr_exp), p(cols_exp),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))  # fmt: skip
+        return indptr_exp, cols_exp
     if bs > 1:
         m = indptr[1:] - indptr[:-1]
         E = (cols.to(torch.int64)[:, None] * bs + torch.arange(bs, device=dev)[None, :]).reshape(-1)
@@ -111,3 +123,25 @@ def build_pattern_torch(dofmap, num_dofs: int, bs: int = 1, chunk_pairs: int = 1
         src = torch.repeat_interleave(start - indptr_exp[:-1], len_exp) + torch.arange(int(indptr_exp[-1]), device=dev)
         indptr, cols = indptr_exp, E[src].to(torch.int32)
     return indptr, cols.contiguous()
+
+
+def add_macro_couplings(indptr, indices, num_dofs: int, bs: int, macro_dofmap):
+    """The pattern (indptr, indices: torch tensors, blocked by ``bs``) plus the couplings of every "macro element"
+    of ``macro_dofmap`` [num_macro, m] (scalar dofs): what dolfinx's create_matrix adds for an interior-facet integral
+    (the two cells of a ghost-penalty facet couple all their dofs, demo/poisson.py:160,168-170).  Returns new
+    (indptr, indices).  Setup code; the union is formed on the tensors' device."""
+    import torch
+
+    dev = indices.device
+    nrows = num_dofs * bs
+    rows = torch.repeat_interleave(torch.arange(nrows, device=dev), indptr[1:] - indptr[:-1])
+    keys = rows * nrows + indices.to(torch.int64)
+    md = torch.as_tensor(macro_dofmap, device=dev).to(torch.int64)
+    blk = torch.arange(bs, device=dev)
+    mr = (md[:, :, None] * bs + blk[None, None, :]).reshape(md.shape[0], -1)  # blocked dofs of every macro element
+    extra = (mr[:, :, None] * nrows + mr[:, None, :]).reshape(-1)
+    keys = torch.unique(torch.cat([keys, extra]))
+    r = torch.div(keys, nrows, rounding_mode="floor")
+    new_indptr = torch.zeros(nrows + 1, dtype=torch.int64, device=dev)
+    new_indptr[1:] = torch.cumsum(torch.bincount(r, minlength=nrows), 0)
+    return new_indptr, (keys - r * nrows).to(torch.int32).contiguous()

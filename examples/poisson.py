@@ -6,7 +6,8 @@ on this package.
 Same steps as the demo: cut-cell quadrature for the level set (here customquad_b200.levelset instead
 of Algoim, demo/poisson.py:88-113), bulk stiffness + load on the uncut cells with a standard Gauss
 rule and ghost penalty on the cut-cell facets (:168-176; dolfinx in the demo), runtime-quadrature
-assembly of the cut bulk part and of the Nitsche boundary terms with quadrature normals (:180-215),
+assembly of the cut bulk part and of the Nitsche boundary terms with quadrature normals (:180-215) -- all of it,
+ghost penalty included, added into one device CSR --,
 inactive-dof locking (:229-232), a direct solve (:239-256; scipy here), L2 / H10 errors and the
 area / volume functionals through assemble_scalar (:266-290).
 
@@ -66,15 +67,17 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
     qr_bulk = [(cut_cells, qr_pts, qr_w)] if device_rules is None else [device_rules[0]]
     qr_bdry = [(cut_cells, qr_pts_bdry, qr_w_bdry, qr_n)] if device_rules is None else [device_rules[1]]
 
-    # matrices: uncut bulk + cut bulk + Nitsche boundary (A = Ax + Ac1 + Ac2, :203-205)
-    A = cq.assemble_matrix(forms.stiffness(V), [qr_uncut])
+    # matrices: uncut bulk + ghost penalty (Ax, :168-170) + cut bulk + Nitsche boundary (A = Ax + Ac1 + Ac2, :203-205),
+    # all into ONE device CSR whose pattern holds the cell couplings and the couplings across the ghost-penalty facets
+    from customquad_b200 import assemble as asm
+
+    facets = cutfem.ghost_penalty_facets(mesh, cut_cells, outside_cells)
+    A = asm.create_matrix(forms.stiffness(V), facets=facets)
+    cq.assemble_matrix(forms.stiffness(V), [qr_uncut], A=A)
+    cutfem.ghost_penalty(V, facets, betas, A)  # betas * avg(h) * [n.grad u][n.grad v] dS(ghost_penalty_tag)
+    cq.assemble_matrix(forms.stiffness(V), qr_bulk, A=A)
+    cq.assemble_matrix(forms.nitsche(V, betaN), qr_bdry, A=A)
     A.assemble()
-    Ac1 = cq.assemble_matrix(forms.stiffness(V), qr_bulk)
-    Ac1.assemble()
-    Ac2 = cq.assemble_matrix(forms.nitsche(V, betaN), qr_bdry)
-    Ac2.assemble()
-    A += Ac1
-    A += Ac2
     # right-hand side: bx + bc1 + bc2 (:208-215); load with a degree-4 rule for the sine source
     b = cq.assemble_vector(forms.load(V, f), [cutfem.standard_rule(mesh, uncut_cells, 4)])
     b += cq.assemble_vector(forms.load(V, f), qr_bulk)
@@ -83,10 +86,8 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
 
     inactive = cutfem.get_inactive_dofs(V, cut_cells, uncut_cells)
     A = cutfem.lock_inactive_dofs(inactive, A)
-    # ghost penalty (host, off the accelerated path) and the direct solve
-    S = cutfem.ghost_penalty_matrix(V, cutfem.ghost_penalty_facets(mesh, cut_cells, outside_cells), betas)
-    Ah = (A.to_scipy() + S).tocsc()
-    uh = cq.Function(V, spla.spsolve(Ah, b.array))
+    # the complete operator leaves the GPU once, for the direct solve (the solver is not part of the path)
+    uh = cq.Function(V, spla.spsolve(A.to_scipy().tocsc(), b.array))
     assert np.isfinite(uh.array).all()
 
     def assemble(make_form):

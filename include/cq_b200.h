@@ -148,6 +148,15 @@ typedef struct cq_quadrature {
   const double* pts;
   const double* weights;
   const double* normals;
+  /* Optional traversal hint (0 = none; never changes the result beyond FP64 summation order).  When the list walks a
+   * structured 3-D mesh plane by plane (plane_entries consecutive entries per cell layer, entry 0 at the start of a
+   * layer), a matrix whose dof planes are larger than the L2 is scattered into twice per plane from DRAM: once per
+   * adjacent cell layer.  With plane_tiles > 1 the persistent kernels walk the list tile by tile instead -- for each
+   * of plane_tiles groups of rows, all layers -- so that the rows a tile scatters into stay in L2 between two
+   * consecutive layers (config 5: 512^2-cell layers, 57 MB of matrix rows per dof plane). */
+  int64_t plane_entries;
+  int32_t plane_tiles;
+  int32_t pad_;
 } cq_quadrature;
 
 /* CSR matrix with the layout dolfinx.cpp.fem.petsc.create_matrix gives an AIJ Mat
@@ -234,6 +243,28 @@ int cq_mesh_classify(cq_ctx* ctx, int cell_type, const cq_mesh* mesh, int32_t* f
 int cq_scatter_map_stride(int cell_type, int degree);
 int cq_build_scatter_map(cq_ctx* ctx, int cell_type, int degree, int bs, int64_t num_cells,
                          const int32_t* dofmap, const cq_csr* A, uint8_t* out, void* stream);
+
+/* ---- blocked pattern (setup, not the timed path) -------------------------------------------------
+ * The AIJ pattern of a blocked space (VectorFunctionSpace, bs = gdim; demo/vector_poisson.py:95) from the pattern of
+ * its scalar space: blocked row r*bs + a holds the columns c*bs + b, b < bs, of every scalar coupling (r, c)
+ * (utils.py:59-62 interleaving; what dolfinx's create_matrix gives a PETSc AIJ Mat with block size bs).
+ *   indptr_out [num_rows*bs + 1] int64, indices_out [indptr[num_rows]*bs*bs] int32 (device, caller-allocated).
+ * One pass, no temporaries: config 4 (Q2 hexahedra 128^3, bs = 3) expands 1.08e9 scalar couplings into 9.69e9. */
+int cq_csr_expand_blocks(cq_ctx* ctx, int64_t num_rows, const int64_t* indptr, const int32_t* indices, int bs,
+                         int64_t* indptr_out, int32_t* indices_out, void* stream);
+
+/* ---- ghost penalty (the step beside the path) ---------------------------------------
+ * betas * avg(h) * inner(jump(n, grad u), jump(n, grad v)) * dS(ghost_penalty_tag) (demo/poisson.py:160,168-170;
+ * demo/vector_poisson.py:127 per component), which the reference leaves to dolfinx's standard assembler, on the
+ * interior facets utils.get_facetags tags (utils.py:155-182), added into the same device CSR as the runtime-
+ * quadrature terms so that A = Ax + Ac1 + Ac2 never leaves the GPU.  Axis-aligned cells (cq_mesh.flags must carry
+ * CQ_MESH_AXIS_ALIGNED), Lagrange degree 1 or 2, bs >= 1 (block-diagonal).
+ *   facets [num_facets, 3] int32 on the device: (cell on the low side, cell on the high side, axis of the normal).
+ * The pattern of A has to contain the couplings between the dofs of the two cells of every facet
+ * (customquad_b200/sparsity.py:add_macro_couplings); a missing slot sets the sparsity error flag (cq_ctx_check). */
+int cq_assemble_ghost_penalty(cq_ctx* ctx, int cell_type, int degree, int bs, double betas, const cq_mesh* mesh,
+                              const cq_space* space, int64_t num_facets, const int32_t* facets, const cq_csr* A,
+                              void* stream);
 
 /* ---- parity / debug hooks --------------------------------------------------------------- */
 /* call_basix for every point of `qr`: out [num_points, nbf] = D^alpha psi_j(xi_q) with

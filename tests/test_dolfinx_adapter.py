@@ -135,3 +135,82 @@ def test_adapter_rejects_what_the_reference_cannot_do():
         dx.function_space(dV)
     with pytest.raises(ValueError):
         dx.form(fake_dolfinx(V)[0], "curlcurl")
+
+
+# ---- UFL integrand -> form menu (dolfinx_adapter.classify_integrand) with stand-in nodes carrying UFL's class names ----
+class _Node:
+    def __init__(self, *ops):
+        self.ufl_operands = ops
+
+
+def _ufl(name):
+    return type(name, (_Node,), {})
+
+
+_Sum, _Product, _Inner, _Dot, _Grad, _NablaGrad, _Division, _Power, _CellDiameter, _FacetNormal, _SpatialCoordinate = (
+    _ufl(n) for n in "Sum Product Inner Dot Grad NablaGrad Division Power CellDiameter FacetNormal SpatialCoordinate".split()
+)
+
+
+class Argument(_Node):
+    def __init__(self, number):
+        super().__init__()
+        self._n = number
+
+    def number(self):
+        return self._n
+
+
+class Coefficient(_Node):
+    pass
+
+
+def test_ufl_integrands_of_the_reference_are_recognised():
+    from customquad_b200 import dolfinx_adapter as dx
+
+    u, v, n, h, g = Argument(1), Argument(0), _FacetNormal(), _CellDiameter(), Coefficient()
+    neg = lambda e: _Product(-1, e)  # noqa: E731  (UFL writes -x as a product with IntValue(-1))
+    assert dx.classify_integrand(_Inner(u, v)) == ("mass", {})  # test/common.py:91
+    assert dx.classify_integrand(_Product(u, v)) == ("mass", {})
+    assert dx.classify_integrand(_Inner(_Grad(u), _Grad(v))) == ("stiffness", {})  # demo/poisson.py:154
+    assert dx.classify_integrand(_Inner(_NablaGrad(u), _NablaGrad(v))) == ("stiffness", {})  # demo/vector_poisson.py:121
+    a_bdry = _Sum(_Sum(neg(_Inner(_Dot(n, _Grad(u)), v)), neg(_Inner(u, _Dot(n, _Grad(v))))), _Inner(_Product(_Division(10.0, h), u), v))
+    assert dx.classify_integrand(a_bdry) == ("nitsche", {"betaN": 10.0})  # demo/poisson.py:156-158
+    L_bdry = _Sum(neg(_Inner(g, _Dot(n, _Grad(v)))), _Inner(_Product(_Division(7.5, h), g), v))
+    kind, data = dx.classify_integrand(L_bdry)  # demo/poisson.py:159
+    assert kind == "nitsche_rhs" and data["betaN"] == 7.5 and data["f"] is g
+    kind, data = dx.classify_integrand(_Inner(g, v))  # test/common.py:66-68
+    assert kind == "load" and data["f"] is g
+    assert dx.classify_integrand(_Product(1.0, v)) == ("load", {"f": 1.0})  # test_linear_basis.py:129
+    assert dx.classify_integrand(1.0) == ("integral", {"f": 1.0})  # test_volume_area.py:58
+    for e in (_Product(g, g), _Inner(g, g), _Power(g, 2)):  # test/common.py:42-44
+        kind, data = dx.classify_integrand(e)
+        assert kind == "integral_sq" and data["f"] is g
+
+
+def test_ufl_integrands_outside_the_menu_raise():
+    from customquad_b200 import dolfinx_adapter as dx
+
+    u, v, n, h = Argument(1), Argument(0), _FacetNormal(), _CellDiameter()
+    for e in (_Inner(_Grad(u), v),                                  # convection-like
+              _Inner(_Product(_SpatialCoordinate(), u), v),        # variable coefficient
+              _Sum(_Inner(u, v), _Inner(_Grad(u), _Grad(v))),      # two menu forms in one integrand
+              _Product(_Division(10.0, h), _Inner(u, v))):          # Nitsche penalty alone
+        with pytest.raises(NotImplementedError):
+            dx.classify_integrand(e)
+
+
+def test_form_from_ufl_builds_the_same_form_as_the_named_constructor():
+    from customquad_b200 import dolfinx_adapter as dx
+    from customquad_b200.forms import FormKind
+
+    mesh = cq.create_rectangle([[0, 0], [1, 1]], [3, 2])
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    u, v, n, h = Argument(1), Argument(0), _FacetNormal(), _CellDiameter()
+    neg = lambda e: _Product(-1, e)  # noqa: E731
+    assert dx.form_from_ufl(_Inner(_Grad(u), _Grad(v)), V).kind == FormKind.STIFFNESS
+    a = dx.form_from_ufl(_Sum(_Sum(neg(_Inner(_Dot(n, _Grad(u)), v)), neg(_Inner(u, _Dot(n, _Grad(v))))), _Inner(_Product(_Division(10.0, h), u), v)), V)
+    assert a.kind == FormKind.NITSCHE and a.betaN == 10.0
+    f = cq.Function(V)
+    assert dx.form_from_ufl(_Inner(f, v), V).coefficient is f
+    assert dx.form_from_ufl(1.0, dmesh=mesh).kind == FormKind.INTEGRAL

@@ -70,3 +70,41 @@ def test_poisson_sphere_converges(cuda_backend):
     rate_h1 = [np.log(h1[i] / h1[i + 1]) / np.log(hs[i] / hs[i + 1]) for i in range(2)]
     assert min(rate_l2) > 1.6, (l2, rate_l2)
     assert min(rate_h1) > 0.8, (h1, rate_h1)
+
+
+@pytest.mark.parametrize("tdim,degree,bs", [(2, 1, 1), (2, 2, 1), (2, 1, 2), (3, 1, 1), (3, 2, 3)])
+def test_ghost_penalty_kernel_matches_host_statement(cuda_backend, tdim, degree, bs):
+    """cq_assemble_ghost_penalty (CUDA, into the device CSR on a facet-coupled pattern) against cutfem.ghost_penalty_matrix
+    (numpy / scipy, its own tabulation) on the facets around a band of "cut" cells."""
+    import scipy.sparse as sp
+
+    import customquad_b200 as cq
+    from customquad_b200 import assemble as asm, cutfem, forms
+
+    mesh = cq.create_rectangle([[-1.0, -2.0], [2.0, 1.5]], [9, 7]) if tdim == 2 else cq.create_box([[-1.0, -2.0, 0.0], [2.0, 1.5, 1.0]], [5, 4, 3])
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(mesh.num_cells)
+    cut, outside = perm[: mesh.num_cells // 3], perm[mesh.num_cells // 3 : mesh.num_cells // 2]
+    facets = cutfem.ghost_penalty_facets(mesh, cut, outside)
+    assert len(facets) > 4
+    V = cq.FunctionSpace(mesh, ("Lagrange", degree), bs)
+    A = asm.create_matrix(forms.stiffness(V), facets=facets)
+    cutfem.ghost_penalty(V, facets, 0.7, A)
+    A.assemble()  # raises if a facet coupling were missing from the pattern
+    S = cutfem.ghost_penalty_matrix(cq.FunctionSpace(mesh, ("Lagrange", degree)), facets, 0.7)
+    S = sp.kron(S, sp.identity(bs), format="csr")
+    D = (A.to_scipy() - S).tocoo()
+    assert np.max(np.abs(D.data)) <= 1e-12 * np.max(np.abs(S.data))
+    # the facet-coupled pattern is a superset of the cell pattern, and the runtime-quadrature path still scatters into it
+    A0 = asm.create_matrix(forms.stiffness(V))
+    assert A.nnz > A0.nnz
+    from customquad_b200.quadrature import synthetic_ragged
+    from oracle import oracle
+
+    qr = synthetic_ragged(np.arange(mesh.num_cells), tdim, 1, 9, seed=2)
+    A.data.zero_()
+    cq.assemble_matrix(forms.stiffness(V), [qr], A=A)
+    A.assemble()
+    R = oracle.assemble_matrix(forms.stiffness(V), [qr])
+    D = (A.to_scipy() - R).tocoo()
+    assert np.max(np.abs(D.data)) <= 1e-12 * np.max(np.abs(R.data))

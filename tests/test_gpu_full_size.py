@@ -160,3 +160,41 @@ def test_config4_shape_hex_q2_vector(cuda_backend):
     b = cq.assemble_vector(forms.load(V, f), [qr]).array
     r = oracle.assemble_vector(forms.load(V, f), [qr], nthreads=oracle.max_threads())
     assert np.max(np.abs(b - r)) <= RTOL * np.max(np.abs(r))
+
+
+def test_long_list_takes_the_ticket_path(cuda_backend):
+    """Lists longer than 512 rounds of grid x slots stages draw their stages from a ticket counter (cq_launch.cuh:
+    choose_dynamic, the config-5 regime) instead of the static interleaving.  1.2e7 one-point entries on a 3500^2 Q1
+    mesh: linearity, total mass, and the oracle on a sample of cells."""
+    from oracle import oracle
+
+    N = 3500
+    mesh = cq.create_rectangle([[-1.11, -1.51], [1.55, 1.22]], [N, N])
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 2, 1, 1, seed=3)
+    assert qr.num_entries > 512 * 148 * 4 * 32
+    M = cq.assemble_matrix(forms.mass(V), [qr])
+    M.assemble()
+    cell_vol = float(np.prod(mesh.h()))
+    assert abs(float(M.data.sum()) - cell_vol * qr.w.sum()) <= RTOL * abs(float(M.data.sum()))
+    K = cq.assemble_matrix(forms.stiffness(V), [qr])
+    K.assemble()
+    assert float(_row_sums(K).abs().max()) <= RTOL * float(K.data.abs().max()) * 25
+    # the full-list matrices themselves against the oracle: rows of the dofs strictly inside a block of cells get all
+    # their contributions from that block, so the oracle on the block's entries must reproduce those rows of K and M
+    for a, b0, m in ((100, 2000, 160), (3300, 37, 160)):
+        ix, iy = np.meshgrid(np.arange(a, a + m), np.arange(b0, b0 + m), indexing="ij")
+        block = (ix * N + iy).reshape(-1)  # cell id = ix * ny + iy
+        sub = qr.select(block)
+        di, dj = np.meshgrid(np.arange(a + 1, a + m), np.arange(b0 + 1, b0 + m), indexing="ij")
+        rows = (di * (N + 1) + dj).reshape(-1)  # Q1 dof id = i * (ny + 1) + j
+        for form, A in ((forms.stiffness(V), K), (forms.mass(V), M)):
+            R = oracle.assemble_matrix(form, [sub], nthreads=oracle.max_threads(), pattern=_cells_pattern(form, sub)).tocsr()
+            ip = A.indptr.cpu().numpy()
+            sel = torch.as_tensor((ip[rows][:, None] + np.arange(9)[None, :]).reshape(-1), device=A.data.device)  # interior rows hold 9 entries
+            got_v, got_c = A.data[sel].cpu().numpy(), A.indices[sel].cpu().numpy()
+            ref = R[rows]
+            assert np.array_equal(np.diff(ref.indptr), np.full(len(rows), 9)) and np.array_equal(ref.indices, got_c)
+            assert np.max(np.abs(got_v - ref.data)) <= RTOL * np.max(np.abs(ref.data))
+    b = cq.assemble_vector(forms.load(V, 1.0), [qr]).array  # the vector kernels share the producer
+    assert abs(b.sum() - cell_vol * qr.w.sum()) <= RTOL * abs(b.sum())

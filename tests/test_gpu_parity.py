@@ -346,3 +346,29 @@ def test_host_buffer_entry_points(cuda_backend, oracle_backend):
     assert close(bh, oracle_backend.vector(lf, [qr]))
     m = asm.assemble_scalar_host(forms.integral(mesh, 1.0), qr)
     assert abs(m - oracle_backend.scalar(forms.integral(mesh, 1.0), [qr])) <= RTOL * abs(m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,degree", [((6, 24, 5), 1), ((13, 19, 7), 1), ((4, 16, 3), 2)])
+def test_plane_tile_traversal_hint(cuda_backend, oracle_backend, monkeypatch, shape, degree):
+    """cq_quadrature.plane_entries / plane_tiles: the persistent kernels walk a layer-by-layer list tile by tile (a
+    bijection of the stages, kernels.cuh:stage_of).  Same matrices as the oracle, for exact and drifting planes
+    (per-layer cell counts that are / are not multiples of the 32-entry stage) and with a partial last stage."""
+    from customquad_b200 import assemble as asm
+
+    mesh = cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], list(shape))
+    V = cq.FunctionSpace(mesh, ("Lagrange", degree))
+    qr = synthetic_ragged(np.arange(mesh.num_cells), 3, 1, 12, seed=23, normals=True)
+    monkeypatch.setattr(asm, "L2_TILE_BYTES", 1)  # every matrix "exceeds the L2": as many tiles as the hint allows
+    form = forms.stiffness(V)
+    A = asm.create_matrix(form)
+    c = asm._Call(form, qr, asm._dev(), A=A)
+    assert c.qr.plane_entries == shape[0] * shape[1] and c.qr.plane_tiles == shape[1] // 2 > 1
+    for form in (forms.stiffness(V), forms.mass(V), forms.nitsche(V, 10.0)):
+        R = oracle_backend.matrix(form, [qr])
+        S = cuda_backend.matrix(form, [qr])
+        assert np.array_equal(S.indptr, R.indptr) and np.array_equal(S.indices, R.indices)
+        assert close(S.data, R.data), form.kind.name
+    # a list that does not start at a layer boundary, or is not consecutive, gets no hint
+    sub = synthetic_ragged(np.arange(3, mesh.num_cells), 3, 1, 4, seed=1)
+    assert asm._Call(forms.mass(V), sub, asm._dev(), A=A).qr.plane_tiles == 0
