@@ -153,7 +153,12 @@ def _traversal_hint(mesh, q, cells_dev, A):
     tiles = int(np.ceil(live / L2_TILE_BYTES))
     if tiles <= 1:
         return 0, 0
-    return per_layer, min(tiles, max(1, int(mesh.shape[1]) // 2))  # at least two cell rows per tile
+    tiles = min(tiles, max(1, int(mesh.shape[1]) // 2))  # at least two cell rows per tile
+    # whole cell rows per tile when the mesh allows it: the next divisor of the row count
+    ny = int(mesh.shape[1])
+    while tiles < ny // 2 and ny % tiles:
+        tiles += 1
+    return per_layer, tiles
 
 
 # ---- descriptors --------------------------------------------------------------------------------

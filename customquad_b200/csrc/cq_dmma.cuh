@@ -140,10 +140,21 @@ CQ_DEVINL void dmma_lane_dofs(const int g, int (&lat)[4][3], bool (&valid)[4]) {
   }
 }
 
-// staged kernel, MODE 2: one warp per stage entry; everything comes from the stage header
+// staged kernel, MODE 2: one warp per stage entry; everything comes from the stage header.
+//
+// Scatter: the accumulator fragments hold one value per (row group, column pair) -- scattered straight from the
+// registers (round 1), a RED instruction's 32 lanes hit 8 rows x 4 column pairs, i.e. ~30 different lines, and every
+// value needed its own scatter position / row start / row length from shared memory: ~8000 LSU wavefronts per cell,
+// the bound of config 4 (Q2, bs = 3: 2187 values per cell).  Now the warp parks the symmetric 27 x 27 block in a
+// shared-memory tile of its own and scatters it ROW BY ROW with lane = local column: the 27 values of a row go to 9
+// runs of 3 consecutive columns (x-neighbours are numbered consecutively), ~10 lines per instruction, and the row's
+// start / length are one broadcast load per row instead of one per value.
+constexpr int DMMA_TILE_STRIDE = 28;                               // doubles per row of the 27 x 27 tile
+constexpr int DMMA_TILE_BYTES = (27 * DMMA_TILE_STRIDE * 8 + 127) / 128 * 128;
+
 template <class T, int CB>
-CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e) {
-  constexpr int N = 27, FORM = T::FORM_ID;
+CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
+  constexpr int N = 27, FORM = T::FORM_ID, TS = DMMA_TILE_STRIDE;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   int lat[4][3];
   bool valid[4];
@@ -159,7 +170,8 @@ CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, c
   const double gamma = FORM == CQ_FORM_NITSCHE ? P.betaN / geo.hK : 0.0;
   double D[10][2];
   dmma_cell_tiles<FORM>(D, geo, gamma, M.pts[e], M.w[e], T::NEED_NORMAL ? M.nrm[e] : nullptr, M.nq[e], t, lat, valid);
-  const int bs = P.bs;
+  // fragments -> tile (both triangles)
+  __syncwarp();  // the previous entry's scatter has read the tile
   int en = 0;
 #pragma unroll
   for (int ti = 0; ti < 4; ++ti)
@@ -170,20 +182,29 @@ CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, c
       for (int c = 0; c < 2; ++c) {
         const int j = 8 * tj + 2 * t + c;
         if (i < N && j < N) {
-          const double v = D[en][c];
-          const int pij = M.pos[e][i * N + j];
-          const long long si = M.rowstart[e][i];
-          const int li = M.rowlen[e][i];
-          for (int a = 0; a < bs; ++a) red_add_f64(P.values + si + (long long)a * li + pij * bs + a, v);
-          if (ti != tj) {  // diagonal tiles are full
-            const int pji = M.pos[e][j * N + i];
-            const long long sj = M.rowstart[e][j];
-            const int lj = M.rowlen[e][j];
-            for (int a = 0; a < bs; ++a) red_add_f64(P.values + sj + (long long)a * lj + pji * bs + a, v);
-          }
+          tile[i * TS + j] = D[en][c];
+          if (ti != tj) tile[j * TS + i] = D[en][c];  // diagonal tiles are full
         }
       }
     }
+  __syncwarp();
+  // row-by-row scatter, lane = local column
+  const int bs = P.bs;
+  if (lane < N) {
+    const uint8_t* pos = &M.pos[e][lane];
+#pragma unroll 3
+    for (int i = 0; i < N; ++i) {
+      const double v = tile[i * TS + lane];
+      const unsigned p = pos[i * N];
+      double* row = P.values + M.rowstart[e][i] + p * bs;
+      if (bs == 1) {
+        red_add_f64(row, v);
+      } else {
+        const int len = M.rowlen[e][i];
+        for (int a = 0; a < bs; ++a) red_add_f64(row + (long long)a * len + a, v);
+      }
+    }
+  }
 }
 
 template <int FORM, int THREADS>

@@ -68,9 +68,11 @@ static int prepare_fused_zero(cq_ctx* ctx, KParams& P, const int n, const int gr
 #ifndef CQ_DYNAMIC_ROUNDS
 #define CQ_DYNAMIC_ROUNDS 512
 #endif
-static int choose_dynamic(cq_ctx* ctx, KParams& P, const int64_t num_stages, const int64_t per_round, cudaStream_t s) {
+// heavy: stages that take so long (Q2 hexahedra: a 27 x 27 tensor-core contraction and 729 bs scattered values per
+// entry) that the ticket's round trip is noise -- always dynamic (measured on config 4, 128^3: 68.7 -> 61.7 ms).
+static int choose_dynamic(cq_ctx* ctx, KParams& P, const int64_t num_stages, const int64_t per_round, cudaStream_t s, const bool heavy = false) {
   const int mode = CQ_TUNE_INT("CQ_DYNAMIC", -1);  // profiling builds: 0 / 1 force
-  P.dynamic = mode >= 0 ? mode : (num_stages > (int64_t)CQ_DYNAMIC_ROUNDS * per_round ? 1 : 0);
+  P.dynamic = mode >= 0 ? mode : ((heavy && num_stages > per_round) || num_stages > (int64_t)CQ_DYNAMIC_ROUNDS * per_round ? 1 : 0);
   if (!P.dynamic) return CQ_OK;
   return check_cuda(cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int), s), "memset(work_counter)");
 }
@@ -110,7 +112,9 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   using Lay = StagedLayout<T, CB>;
   auto kernel = assemble_staged_kernel<T, G, NPW, NCW, MODE>;
   // stage capacity: ~1.25x the mean points of 32 entries, bounded by the shared memory per SM
-  const size_t budget = (size_t)ctx->max_smem_optin - 1024;
+  // (MODE 2: every consumer warp also owns a 27 x 27 tile for the row-by-row scatter, cq_dmma.cuh)
+  const size_t tiles = MODE == 2 ? (size_t)NCW * DMMA_TILE_BYTES : 0;
+  const size_t budget = (size_t)ctx->max_smem_optin - 1024 - tiles;
   const size_t per_point = (size_t)T::DIM * 8 * (T::NEED_NORMAL ? 2 : 1) + 8;
   const size_t fixed = Lay::meta_bytes + 3 * 128 + 2 * per_point;
   if (budget / NPW <= fixed + 64 * per_point) { set_error("staged kernel: stage header does not fit shared memory"); return CQ_ERR_UNSUPPORTED; }
@@ -122,11 +126,11 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   if (pb < 64) pb = 64;
   P.stage_points = (int)pb;
   P.dbg = CQ_TUNE_INT("CQ_DEBUG", 0);
-  const size_t smem = NPW * Lay::stage_bytes((int)pb);
+  const size_t smem = NPW * Lay::stage_bytes((int)pb) + tiles;
   if (int rc = ensure_smem_optin(ctx, (const void*)kernel, smem)) return rc;
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
-  if (int rc = choose_dynamic(ctx, P, num_stages, grid * NPW, s)) return rc;
+  if (int rc = choose_dynamic(ctx, P, num_stages, grid * NPW, s, MODE == 2)) return rc;
   kernel<<<grid, (NPW + NCW) * 32, smem, s>>>(P);
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");

@@ -34,7 +34,7 @@ static int launch_matrix_form(cq_ctx* ctx, const cq_form_desc& f, const KParams&
   // Q2 hexahedron: FP64 tensor-core contraction, staged (warp per entry) when the scatter map is there
   using TQ2 = FormTraits<FORM, 3, 2, 1, CQ_FN_CONST>;
   if (staged_ok<TQ2>(ctx, P)) {
-    constexpr int NPW = TQ2::NEED_NORMAL ? 2 : 3;
+    constexpr int NPW = 2;  // two stage slots: the consumer warps' scatter tiles take up to 78 KB of the shared memory
     return P.bs == 1 ? launch_staged<TQ2, 32, NPW, CQ_DMMA_NCW, 2>(ctx, P, s)
                      : launch_staged<TQ2, 32, NPW, CQ_DMMA_NCW_BLOCKED, 2>(ctx, P, s);
   }

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
             if (e0 >= nent) break;
             const bool active = e0 + grp < nent;
             const int e = active ? M.order[e0 + grp] : 0;
-            if constexpr (MODE == 2) dmma_process_entry<T, CB>(P, M, e);
+            if constexpr (MODE == 2) dmma_process_entry<T, CB>(P, M, e, reinterpret_cast<double*>(smem_raw + (size_t)NPW * stage_bytes + (size_t)(warp - NPW) * DMMA_TILE_BYTES));
             else if constexpr (MODE == 1) moment_process_entry<T, G, CB>(P, M, e, active, r);
             else staged_process_entry<T, G, CB>(P, M, e, active, r, msum, LE);
           }
