@@ -34,6 +34,10 @@ struct cq_ctx {
   int fused_zero = 0;   // cq_ctx_set_fused_zero
   void* zero_buf = nullptr;
   size_t zero_waves = 0;
+  // cut-cell producers: compacted list of the cells the box test calls cut (+ its length), grow-only
+  int32_t* cut_list = nullptr;
+  size_t cut_list_cap = 0;
+  unsigned int* cut_count = nullptr;
   // multi-GPU (cq_comm.cu): NCCL communicator (resolved at run time), receive buffer, neighbour fence through peer memory
   void* nccl_comm = nullptr;
   int comm_rank = -1, comm_size = 0;

@@ -345,13 +345,14 @@ def _produce_on_device(mesh, D, classify, rules, gdim):
     f64 = lambda n: torch.empty(max(n, 1), dtype=torch.float64, device=dev)[:n]  # noqa: E731
     pts, w, pts_b, w_b, nrm = f64(gdim * Pb), f64(Pb), f64(gdim * Ps), f64(Ps), f64(gdim * Ps)
     _lib.check(rules(ctx, C.byref(D), ncut, p(cut), p(off_b), p(off_s), p(pts), p(w), p(pts_b), p(w_b), p(nrm), stream))
+    # the rules are born on the device and stay there (``q.host()`` copies them back on demand: at 256^3 the copies of
+    # 25 M points into pageable memory were most of round 1's 511 ms "producer time"); only the cell lists go back
+    qb = RaggedQuadrature.on_device(cut, off_b, pts, w, None, gdim)
+    qs = RaggedQuadrature.on_device(cut, off_s, pts_b, w_b, nrm, gdim)
     host = lambda t: t.cpu().numpy()  # noqa: E731
-    qb = RaggedQuadrature(host(cut), host(off_b), host(pts), host(w), None, gdim)
-    qs = RaggedQuadrature(host(cut), host(off_s), host(pts_b), host(w_b), host(nrm), gdim)
-    qb._dev[dev] = (cut, off_b, pts, w, None)
-    qs._dev[dev] = (cut, off_s, pts_b, w_b, nrm)
-    c = host(cls)
-    return (host(cut), np.nonzero(c == 2)[0].astype(np.int32), np.nonzero(c == 0)[0].astype(np.int32), qb, qs)
+    uncut = torch.nonzero(cls == 2).reshape(-1).to(torch.int32)
+    outside = torch.nonzero(cls == 0).reshape(-1).to(torch.int32)
+    return (host(cut), host(uncut), host(outside), qb, qs)
 
 
 def generate_qr_sphere_device(mesh, radius=1.0, center=(0.0, 0.0, 0.0), order=4, axis=2):

@@ -43,7 +43,7 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
         if qr == "device":
             cut, uncut, outside, qb, qs = generate_qr_circle_device(mesh, 1.0, (0.0, 0.0), order)
             device_rules = (qb, qs)
-            rules = (cut, uncut, outside, None, np.split(qb.w, qb.offsets[1:-1]), None, np.split(qs.w, qs.offsets[1:-1]), None)
+            rules = (cut, uncut, outside, None, np.split(qb.host().w, qb.host().offsets[1:-1]), None, np.split(qs.host().w, qs.host().offsets[1:-1]), None)
         else:
             rules = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
     else:
@@ -53,7 +53,7 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
         if qr == "device":
             cut, uncut, outside, qb, qs = generate_qr_sphere_device(mesh, 1.0, (0.0, 0.0, 0.0), order)
             device_rules = (qb, qs)
-            rules = (cut, uncut, outside, None, np.split(qb.w, qb.offsets[1:-1]), None, np.split(qs.w, qs.offsets[1:-1]), None)
+            rules = (cut, uncut, outside, None, np.split(qb.host().w, qb.host().offsets[1:-1]), None, np.split(qs.host().w, qs.host().offsets[1:-1]), None)
         else:
             rules = generate_qr_sphere(mesh, 1.0, (0.0, 0.0, 0.0), order)
     gdim = len(xmin)

@@ -25,6 +25,8 @@ def test_device_producer_matches_host_producer(cuda_backend, box, n, radius, cen
     mesh = cq.create_rectangle(box, n)
     cut, uncut, outside, qp, qw, qpb, qwb, qn = levelset.generate_qr_circle(mesh, radius, center, order)
     dcut, duncut, doutside, qb, qs = levelset.generate_qr_circle_device(mesh, radius, center, order)
+    assert qb.cells is None and qs.cells is None  # born on the device, no host copy until asked for
+    qb, qs = qb.host(), qs.host()
     assert np.array_equal(dcut, cut) and np.array_equal(duncut, uncut) and np.array_equal(doutside, outside)
     assert np.array_equal(np.diff(qb.offsets), [w.size for w in qw])
     assert np.array_equal(np.diff(qs.offsets), [w.size for w in qwb])
@@ -73,6 +75,7 @@ def test_device_sphere_producer_matches_host_producer(cuda_backend, box, n, radi
     mesh = cq.create_box(box, n)
     cut, uncut, outside, qp, qw, qpb, qwb, qn = levelset.generate_qr_sphere(mesh, radius, center, order, axis)
     dcut, duncut, doutside, qb, qs = levelset.generate_qr_sphere_device(mesh, radius, center, order, axis)
+    qb, qs = qb.host(), qs.host()
     assert np.array_equal(dcut, cut) and np.array_equal(duncut, uncut) and np.array_equal(doutside, outside)
     assert np.array_equal(np.diff(qb.offsets), [w.size for w in qw])
     assert np.array_equal(np.diff(qs.offsets), [w.size for w in qwb])
