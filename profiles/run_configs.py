@@ -72,6 +72,8 @@ def run(name, mesh, degree, bs, nq_lo, nq_hi, which, frac_cells=1.0):
 
 if __name__ == "__main__":
     sel = sys.argv[1:] or ["hexq1", "hexq2", "quadnitsche"]
+    if os.environ.get("CQ_VARIANT"):  # 1: the direct (un-staged) kernels
+        asm.set_variant(int(os.environ["CQ_VARIANT"]))
     t0 = time.time()
     if "hexq1" in sel:
         mesh = cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [128, 128, 128])

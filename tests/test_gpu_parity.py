@@ -372,3 +372,41 @@ def test_plane_tile_traversal_hint(cuda_backend, oracle_backend, monkeypatch, sh
     # a list that does not start at a layer boundary, or is not consecutive, gets no hint
     sub = synthetic_ragged(np.arange(3, mesh.num_cells), 3, 1, 4, seed=1)
     assert asm._Call(forms.mass(V), sub, asm._dev(), A=A).qr.plane_tiles == 0
+
+
+def test_far_from_origin_mesh_matches_recentred_oracle(cuda_backend, oracle_backend):
+    """Rank 7's slab of the N = 8 weak-scaling mesh (x ~ 20, h = 1.3e-3: kappa = max|x| / h = 1.6e4).  The reference's
+    J = sum_v x_v grad psi_v carries a rounding error of a few eps * kappa of its own, so on identical inputs the two
+    sides agree to max(1e-12, 4 eps kappa) (bench.py:parity_tolerance); against the oracle on the SAME cells with the
+    geometry translated to the origin (these integrands do not depend on x) the CUDA path agrees to 1e-12: its cell
+    constants come from vertex differences, which are exact.  profiles/r2s2/far_mesh_parity.jsonl."""
+    import bench
+    import customquad_b200 as cq
+    from customquad_b200 import dist as cqdist, forms
+    from customquad_b200.quadrature import synthetic_ragged
+
+    world, ny = 8, 64
+    hx = (bench.XMAX[0] - bench.XMIN[0]) / bench.MESH_N
+    slab = cqdist.make_slab([[bench.XMIN[0], bench.XMIN[1]], [bench.XMIN[0] + bench.MESH_N * world * hx, bench.XMIN[1] + ny * hx]],
+                            [bench.MESH_N * world, ny], world - 1, world)  # fmt: skip
+    mesh = slab.mesh
+    tol, kappa = bench.parity_tolerance(mesh)
+    assert kappa > 1e4 and tol < 2e-11
+    cells = np.arange(8 * ny, dtype=np.int32)
+    qr = synthetic_ragged(cells, 2, 16, 64, seed=11)
+    x = mesh.geometry.x
+    for deg in (1, 2):
+        V = cq.FunctionSpace(mesh, ("Lagrange", deg))
+        for name in ("stiffness", "mass"):
+            f = getattr(forms, name)(V)
+            S = cuda_backend.matrix(f, [qr])
+            R = oracle_backend.matrix(f, [qr])
+            try:
+                mesh.geometry.x = x - np.array([x[:, 0].min(), 0.0, 0.0])
+                R0 = oracle_backend.matrix(f, [qr])
+            finally:
+                mesh.geometry.x = x
+            assert np.array_equal(S.indices, R.indices) and np.array_equal(S.indptr, R.indptr)
+            sc = np.abs(R0.data).max()
+            assert np.abs(S.data - R.data).max() <= tol * sc
+            assert np.abs(S.data - R0.data).max() <= 1e-12 * sc
