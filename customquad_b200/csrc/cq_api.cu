@@ -392,6 +392,7 @@ int cq_ctx_destroy(cq_ctx* ctx) {
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->scalar_dev) cudaFree(ctx->scalar_dev);
   if (ctx->zero_buf) cudaFree(ctx->zero_buf);
+  if (ctx->owner_ws) cudaFree(ctx->owner_ws);
   if (ctx->cut_list) cudaFree(ctx->cut_list);
   if (ctx->cut_count) cudaFree(ctx->cut_count);
   if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
@@ -443,6 +444,7 @@ static int assemble_matrix_impl(cq_ctx* ctx, const cq_form_desc* form, const cq_
     return CQ_ERR_UNSUPPORTED;
   }
   P.zero_req = zero_first ? 1 : 0;
+  P.num_dofs = space->num_dofs;
   P.nnz = A->nnz;
   P.indptr = A->indptr; P.indices = A->indices; P.values = A->values;
   if (A->peer_rowstart) {

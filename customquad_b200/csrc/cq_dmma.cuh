@@ -30,29 +30,59 @@ CQ_DEVINL void dmma_m8n8k4(double (&d)[2], const double a, const double b) {
                : "d"(a), "d"(b));
 }
 
-CQ_DEVINL double sel3(const double (&v)[3], const int t) { return t == 0 ? v[0] : (t == 1 ? v[1] : v[2]); }
+// ---- point loop ------------------------------------------------------------------------------------------
+// Round 1 let every lane evaluate the 1-D bases of "its" point and pick its dofs' factors out of them with
+// run-time selects: the compiler turned those into divergent branches and local-memory traffic, and the eight lanes
+// that share a point repeated its basis and Jacobian (measured 0.37 of the DMMA peak; the tensor core waited on
+// scalar code).  Now the warp first fills a TABLE in shared memory, one row per point, one lane per point:
+//   [0..8]   l_a(xi_d) at d * 3 + a      [9]  0.0   (the padding dofs 27..31 read the zeros)
+//   [10..18] l_a'(xi_d) at 10 + d * 3 + a [19] 0.0
+//   [20..]   the point's factors: stiffness G = w / |det J| adj adj^T (6 values), mass w |det J|,
+//            Nitsche w |det J|, w |det J| gamma, m = adj n / det J
+// and the k-steps read each lane's factors through per-lane row offsets fixed for the whole kernel.  The table lives
+// in the warp's 27 x 28 scatter tile (28 rows of 27 doubles: a 27-point rule is one chunk).
+// Stiffness: S_ij = sum_q g_i^T G g_j with g the REFERENCE gradient: the A fragment is g itself, the B fragment G g.
+constexpr int DT_STRIDE = 27;  // doubles per table row
+constexpr int DT_POINTS = 28;  // rows: 28 * 27 = 27 * 28 doubles, the scatter tile
 
+// this lane's row offsets: dof 8 * tile + g, factor of dimension d
+CQ_DEVINL void dmma_lane_offsets(const int g, int (&off)[4][3]) {
+#pragma unroll
+  for (int tile = 0; tile < 4; ++tile) {
+    const int j = 8 * tile + g;
+    const int pk = c_q2hex_lat[j];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) off[tile][d] = j < 27 ? d * 3 + ((pk >> (2 * d)) & 3) : 9;
+  }
+}
 
-// point loop of one cell: accumulates the 10 upper-triangular 8x8 tiles D of the scalar 27x27 block.
-// pts / w / nrm: the cell's points (global or shared memory), lat/valid: this lane's four dofs.
 template <int FORM>
-CQ_DEVINL void dmma_cell_tiles(double (&D)[10][2], const CellGeom<3>& geo, const double gamma, const double* pts, const double* w_,
-                               const double* nrm_, const int nq, const int t, const int (&lat)[4][3], const bool (&valid)[4]) {
+CQ_DEVINL void dmma_fill_table(double* __restrict__ tab, const CellGeom<3>& geo, const double gamma, const double* pts, const double* w_,
+                               const double* nrm_, const int q0, const int nqc, const int lane) {
+  const int rows = (nqc + 3) & ~3;
+  for (int r = lane; r < rows; r += 32) {
+    double* __restrict__ row = tab + r * DT_STRIDE;
+    if (r >= nqc) {  // padding point of the last k-step: contributes nothing
 #pragma unroll
-  for (int i = 0; i < 10; ++i) D[i][0] = D[i][1] = 0.0;
-  for (int qb = 0; qb < nq; qb += 4) {
-    const int q = qb + t;
-    const bool live = q < nq;
-    double xi[3] = {0.5, 0.5, 0.5}, nrm[3] = {0.0, 0.0, 0.0}, w = 0.0;
-    if (live) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) xi[d] = pts[3 * q + d];
-      w = w_[q];
-      if constexpr (FORM == CQ_FORM_NITSCHE)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) nrm[d] = nrm_[3 * q + d];
+      for (int i = 0; i < DT_STRIDE; ++i) row[i] = 0.0;
+      continue;
     }
-    const Basis1D<2> b0(xi[0]), b1(xi[1]), b2(xi[2]);
+    const int q = q0 + r;
+    double xi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xi[d] = pts[3 * q + d];
+    const double w = w_[q];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const Basis1D<2> b(xi[d]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        row[d * 3 + a] = b.v[a];
+        row[10 + d * 3 + a] = b.d[a];
+      }
+    }
+    row[9] = 0.0;
+    row[19] = 0.0;
     double adj[3][3], det;
     if (geo.affine) {  // constant Jacobian: per-cell values
       det = geo.det0;
@@ -67,12 +97,37 @@ CQ_DEVINL void dmma_cell_tiles(double (&D)[10][2], const CellGeom<3>& geo, const
     }
     const double adet = fabs(det);
     if constexpr (FORM == CQ_FORM_MASS) {
-      const double s = w * adet;
+      row[20] = w * adet;
+    } else if constexpr (FORM == CQ_FORM_STIFFNESS) {
+      const double sc = w / adet;
+      int k = 20;
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+#pragma unroll
+        for (int f = e; f < 3; ++f, ++k) row[k] = sc * fma(adj[e][2], adj[f][2], fma(adj[e][1], adj[f][1], adj[e][0] * adj[f][0]));
+    } else {
+      const double s = w * adet, inv_det = 1.0 / det;
+      row[20] = s;
+      row[21] = s * gamma;
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        row[22 + e] = fma(adj[e][2], nrm_[3 * q + 2], fma(adj[e][1], nrm_[3 * q + 1], adj[e][0] * nrm_[3 * q])) * inv_det;
+    }
+  }
+}
+
+// k-steps over the table rows [0, rows): accumulates into the 10 upper-triangular 8x8 tiles D
+template <int FORM>
+CQ_DEVINL void dmma_table_steps(double (&D)[10][2], const double* __restrict__ tab, const int rows, const int t, const int (&off)[4][3],
+                                const bool diagG) {
+  for (int qb = 0; qb < rows; qb += 4) {
+    const double* __restrict__ row = tab + (qb + t) * DT_STRIDE;
+    if constexpr (FORM == CQ_FORM_MASS) {
+      const double s = row[20];
       double f[4], sf[4];
 #pragma unroll
       for (int tile = 0; tile < 4; ++tile) {
-        const double v = sel3(b0.v, lat[tile][0]) * sel3(b1.v, lat[tile][1]) * sel3(b2.v, lat[tile][2]);
-        f[tile] = valid[tile] ? v : 0.0;
+        f[tile] = row[off[tile][0]] * row[off[tile][1]] * row[off[tile][2]];
         sf[tile] = s * f[tile];
       }
       int e = 0;
@@ -81,41 +136,55 @@ CQ_DEVINL void dmma_cell_tiles(double (&D)[10][2], const CellGeom<3>& geo, const
 #pragma unroll
         for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], sf[ti], f[tj]);
     } else if constexpr (FORM == CQ_FORM_STIFFNESS) {
-      const double sc = w / adet;
-      double f[4][3], sf[4][3];
+      double gr[4][3];
 #pragma unroll
       for (int tile = 0; tile < 4; ++tile) {
-        const double v0 = sel3(b0.v, lat[tile][0]), v1 = sel3(b1.v, lat[tile][1]), v2 = sel3(b2.v, lat[tile][2]);
-        const double d0 = sel3(b0.d, lat[tile][0]), d1 = sel3(b1.d, lat[tile][1]), d2 = sel3(b2.d, lat[tile][2]);
-        const double gr[3] = {d0 * v1 * v2, v0 * d1 * v2, v0 * v1 * d2};
+        const double v0 = row[off[tile][0]], v1 = row[off[tile][1]], v2 = row[off[tile][2]];
+        const double d0 = row[off[tile][0] + 10], d1 = row[off[tile][1] + 10], d2 = row[off[tile][2] + 10];
+        gr[tile][0] = d0 * (v1 * v2);
+        gr[tile][1] = (v0 * v2) * d1;
+        gr[tile][2] = (v0 * v1) * d2;
+      }
+      const double G00 = row[20], G11 = row[23], G22 = row[25];
+      if (diagG) {  // axis-aligned cell (every cell of a create_box mesh): G is diagonal
+        const double Gd[3] = {G00, G11, G22};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const double a = fma(adj[2][c], gr[2], fma(adj[1][c], gr[1], adj[0][c] * gr[0]));
-          f[tile][c] = valid[tile] ? a : 0.0;
-          sf[tile][c] = sc * f[tile][c];
+          double b[4];
+#pragma unroll
+          for (int tile = 0; tile < 4; ++tile) b[tile] = Gd[c] * gr[tile][c];
+          int e = 0;
+#pragma unroll
+          for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], gr[ti][c], b[tj]);
+        }
+      } else {
+        const double G01 = row[21], G02 = row[22], G12 = row[24];
+        const double G[3][3] = {{G00, G01, G02}, {G01, G11, G12}, {G02, G12, G22}};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          double b[4];
+#pragma unroll
+          for (int tile = 0; tile < 4; ++tile) b[tile] = fma(G[c][2], gr[tile][2], fma(G[c][1], gr[tile][1], G[c][0] * gr[tile][0]));
+          int e = 0;
+#pragma unroll
+          for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], gr[ti][c], b[tj]);
         }
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        int e = 0;
-#pragma unroll
-        for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-          for (int tj = ti; tj < 4; ++tj, ++e) dmma_m8n8k4(D[e], sf[ti][c], f[tj][c]);
-      }
     } else {  // CQ_FORM_NITSCHE:  psi_i u_j - e_i psi_j,  e = s dn,  u = s gamma psi - e
-      const double s = w * adet, sg = s * gamma, inv_det = 1.0 / det;
-      double m[3];
-#pragma unroll
-      for (int e = 0; e < 3; ++e) m[e] = fma(adj[e][2], nrm[2], fma(adj[e][1], nrm[1], adj[e][0] * nrm[0])) * inv_det;
+      const double s = row[20], sg = row[21], m0 = row[22], m1 = row[23], m2 = row[24];
       double psi[4], ev[4], uv[4];
 #pragma unroll
       for (int tile = 0; tile < 4; ++tile) {
-        const double v0 = sel3(b0.v, lat[tile][0]), v1 = sel3(b1.v, lat[tile][1]), v2 = sel3(b2.v, lat[tile][2]);
-        const double d0 = sel3(b0.d, lat[tile][0]), d1 = sel3(b1.d, lat[tile][1]), d2 = sel3(b2.d, lat[tile][2]);
-        const double dn = fma(m[2], v0 * v1 * d2, fma(m[1], v0 * d1 * v2, m[0] * (d0 * v1 * v2)));
-        psi[tile] = valid[tile] ? v0 * v1 * v2 : 0.0;
-        ev[tile] = valid[tile] ? s * dn : 0.0;
+        const double v0 = row[off[tile][0]], v1 = row[off[tile][1]], v2 = row[off[tile][2]];
+        const double d0 = row[off[tile][0] + 10], d1 = row[off[tile][1] + 10], d2 = row[off[tile][2] + 10];
+        const double v12 = v1 * v2;
+        const double dn = fma(m2, (v0 * v1) * d2, fma(m1, (v0 * v2) * d1, m0 * (d0 * v12)));
+        psi[tile] = v0 * v12;
+        ev[tile] = s * dn;
         uv[tile] = fma(sg, psi[tile], -ev[tile]);
       }
       int e = 0;
@@ -130,13 +199,22 @@ CQ_DEVINL void dmma_cell_tiles(double (&D)[10][2], const CellGeom<3>& geo, const
   }
 }
 
-CQ_DEVINL void dmma_lane_dofs(const int g, int (&lat)[4][3], bool (&valid)[4]) {
+// point loop of one cell: the 10 upper-triangular 8x8 tiles D of the scalar 27x27 block.
+// pts / w / nrm: the cell's points (global or shared memory); tab: the warp's table (all 32 lanes call this).
+template <int FORM>
+CQ_DEVINL void dmma_cell_tiles(double (&D)[10][2], const CellGeom<3>& geo, const double gamma, const double* pts, const double* w_,
+                               const double* nrm_, const int nq, const int lane, const int (&off)[4][3], double* __restrict__ tab) {
 #pragma unroll
-  for (int tile = 0; tile < 4; ++tile) {
-    const int j = 8 * tile + g;
-    const int pk = c_q2hex_lat[j];
-    lat[tile][0] = pk & 3; lat[tile][1] = (pk >> 2) & 3; lat[tile][2] = (pk >> 4) & 3;
-    valid[tile] = j < 27;
+  for (int i = 0; i < 10; ++i) D[i][0] = D[i][1] = 0.0;
+  // diagonal Jacobian of an affine cell: adj is diagonal, and so is G
+  const bool diagG = geo.affine && geo.adj0[0][1] == 0.0 && geo.adj0[0][2] == 0.0 && geo.adj0[1][0] == 0.0 && geo.adj0[1][2] == 0.0 &&
+                     geo.adj0[2][0] == 0.0 && geo.adj0[2][1] == 0.0;
+  for (int q0 = 0; q0 < nq; q0 += DT_POINTS) {
+    const int nqc = nq - q0 < DT_POINTS ? nq - q0 : DT_POINTS;
+    __syncwarp();  // the table's previous readers (k-steps of the last chunk, scatter of the last entry) are done
+    dmma_fill_table<FORM>(tab, geo, gamma, pts, w_, nrm_, q0, nqc, lane);
+    __syncwarp();
+    dmma_table_steps<FORM>(D, tab, (nqc + 3) & ~3, lane & 3, off, diagG);
   }
 }
 
@@ -156,9 +234,8 @@ template <class T, int CB>
 CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, const int e, double* __restrict__ tile) {
   constexpr int N = 27, FORM = T::FORM_ID, TS = DMMA_TILE_STRIDE;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  int lat[4][3];
-  bool valid[4];
-  dmma_lane_dofs(g, lat, valid);
+  int off[4][3];
+  dmma_lane_offsets(g, off);
   double X[8][3];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
@@ -169,9 +246,9 @@ CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, c
   init_affine<3>(geo);
   const double gamma = FORM == CQ_FORM_NITSCHE ? P.betaN / geo.hK : 0.0;
   double D[10][2];
-  dmma_cell_tiles<FORM>(D, geo, gamma, M.pts[e], M.w[e], T::NEED_NORMAL ? M.nrm[e] : nullptr, M.nq[e], t, lat, valid);
+  dmma_cell_tiles<FORM>(D, geo, gamma, M.pts[e], M.w[e], T::NEED_NORMAL ? M.nrm[e] : nullptr, M.nq[e], lane, off, tile);
   // fragments -> tile (both triangles)
-  __syncwarp();  // the previous entry's scatter has read the tile
+  __syncwarp();  // the k-steps have read the table, which lives in the tile
   int en = 0;
 #pragma unroll
   for (int ti = 0; ti < 4; ++ti)
@@ -188,6 +265,16 @@ CQ_DEVINL void dmma_process_entry(const KParams& P, const StageMeta<T, CB>& M, c
       }
     }
   __syncwarp();
+  if (P.elem_scalar != nullptr) {
+    // owner-computes path (cq_owner.cuh): the block leaves as 729 consecutive doubles, row-major, at list position k
+    double* __restrict__ o = P.elem_scalar + (M.k0 + e) * (long long)(N * N);
+#pragma unroll 4
+    for (int idx = lane; idx < N * N; idx += 32) {
+      const int i = idx / N;
+      o[idx] = tile[i * TS + (idx - i * N)];
+    }
+    return;
+  }
   // row-by-row scatter, lane = local column
   const int bs = P.bs;
   if (lane < N) {
@@ -215,9 +302,10 @@ __global__ void __launch_bounds__(THREADS) assemble_q2hex_dmma_kernel(const KPar
   const int64_t warp_id = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
   const int64_t num_warps = (int64_t)gridDim.x * (THREADS / 32);
 
-  int lat[4][3];
-  bool valid[4];
-  dmma_lane_dofs(g, lat, valid);
+  int off[4][3];
+  dmma_lane_offsets(g, off);
+  __shared__ double tab_all[THREADS / 32][DT_POINTS * DT_STRIDE];
+  double* tab = tab_all[threadIdx.x >> 5];
 
   for (int64_t k = warp_id; k < P.num_entries; k += num_warps) {
     const int32_t cell = __ldg(P.cells + k);
@@ -230,8 +318,8 @@ __global__ void __launch_bounds__(THREADS) assemble_q2hex_dmma_kernel(const KPar
     const double gamma = FORM == CQ_FORM_NITSCHE ? P.betaN / geo.hK : 0.0;
 
     double D[10][2];  // upper-triangular tiles (ti <= tj), row-major enumeration
-    dmma_cell_tiles<FORM>(D, geo, gamma, P.pts + 3 * q0, P.w + q0, FORM == CQ_FORM_NITSCHE ? P.normals + 3 * q0 : nullptr, (int)(q1 - q0), t, lat,
-                          valid);
+    dmma_cell_tiles<FORM>(D, geo, gamma, P.pts + 3 * q0, P.w + q0, FORM == CQ_FORM_NITSCHE ? P.normals + 3 * q0 : nullptr, (int)(q1 - q0), lane, off,
+                          tab);
 
     // ---- sink: lane holds D[ti][tj] at row 8*ti + g, cols 8*tj + 2*t + {0,1} -------------------
     const int bs = P.bs;

@@ -47,6 +47,9 @@ struct cq_ctx {
   unsigned int* fence_down = nullptr;   // mapped: the down neighbour's word [1]
   unsigned int* fence_up = nullptr;     // mapped: the up neighbour's word [0]
   unsigned int fence_epoch = 0;
+  // owner-computes path (cq_owner.cuh): element blocks + dof -> entry lists, grow-only
+  void* owner_ws = nullptr;
+  size_t owner_ws_bytes = 0;
   // dynamic shared memory opt-in already granted on this device, per kernel (cq_launch.cuh:ensure_smem_optin)
   std::unordered_map<const void*, size_t> smem_optin;
 };

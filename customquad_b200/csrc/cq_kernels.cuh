@@ -42,6 +42,8 @@ struct KParams {
   int dbg;                               // profiling builds only (-DCQ_PROFILING, CQ_DEBUG): 1 consumers skip all work, 2 skip the scatter
   int bs;          // block size used by the matrix scatter (compile-time BS for rank < 2)
   int elem_out;    // 1: write un-scattered element tensors to out[k, :]
+  double* elem_scalar;  // owner-computes path (cq_owner.cuh): the kernel writes the scalar N x N block of entry k to elem_scalar[k, :] instead of scattering it
+  long long num_dofs;   // scalar dofs of the space (rows / bs)
   // fused A.zeroEntries() (cq_assemble_matrix_zero, cq_zero.cuh): the kernel itself zeroes `values` just ahead of
   // the scatter, so the REDs hit zeroed lines that are still in L2 instead of reading a memset's lines back from HBM
   int zero_req;                          // 1: values are uninitialised, zero them (in the kernel, or by a memset)

@@ -87,6 +87,7 @@ struct StageMeta {
   static constexpr bool VEC = T::RANK == 1;
   int nent;              // entries in this stage, -1: no more work
   int next;              // consumer claim counter
+  long long k0;          // list position of the stage's first entry (element-tensor output of the owner-computes path, cq_owner.cuh)
   int order[CB];         // entry indices sorted by trip count, longest first
   int nq[CB];
   int cell[CB];

@@ -39,6 +39,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
     constexpr int NP16 = (Meta::MAT && !POS_BULK) ? Meta::NPOS / 16 : 1;
     struct Regs {
       long long t;  // stage index; -2: pipeline bubble, -1: no more work
+      long long k0; // list position of the stage's first entry
       int nent;
       bool valid;
       int64_t o0, o1;
@@ -59,6 +60,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
 #endif
     ra.t = rb.t = rc.t = -2;
     ra.valid = rb.valid = rc.valid = false;
+    const bool scat = P.elem_scalar == nullptr;  // owner-computes path: no scatter, so no row starts / scatter map
     // Stages are dealt out statically, interleaved over the CTAs and their slots: with hundreds of
     // stages per CTA the ragged rules average out (a dynamic ticket costs one more dependent
     // round trip per stage in this latency-bound warp).
@@ -111,7 +113,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         if (Pa + cnt_copy > P.num_points) { cnt_copy = cnt - 1; tail = 1; }
         if (lane == 0) {
           const uint32_t b_pts = (uint32_t)(cnt_copy * DIM * 8), b_w = (uint32_t)(cnt_copy * 8);
-          mbar_arrive_expect_tx(full_bar_w, b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w + (POS_BULK ? (uint32_t)(nent * Meta::NPOS) : 0u));
+          mbar_arrive_expect_tx(full_bar_w, b_pts * (T::NEED_NORMAL ? 2u : 1u) + b_w + (POS_BULK && scat ? (uint32_t)(nent * Meta::NPOS) : 0u));
           if (cnt_copy > 0) {
             CQ_BULK_ONCE(s_pts, P.pts + Pa * DIM, b_pts, full_bar_w);
             CQ_BULK_ONCE(s_w, P.w + Pa, b_w, full_bar_w);
@@ -144,7 +146,8 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
 #else
           const bool consec = false;
 #endif
-          if (consec) {
+          if (!scat) {
+          } else if (consec) {
             if (lane == 0) CQ_BULK_ONCE(&M.pos[0][0], P.elem_pos + (int64_t)cell0 * Meta::NPOS, CB * Meta::NPOS, full_bar_w);
           } else if (ra.valid) {
             CQ_BULK_ONCE(&M.pos[lane][0], P.elem_pos + (int64_t)ra.cell * Meta::NPOS, Meta::NPOS, full_bar_w);
@@ -220,6 +223,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         if (lane == 0) {
           M.nent = nent;
           M.next = 0;
+          M.k0 = ra.k0;
         }
         __syncwarp();
         if (lane == 0) {
@@ -245,14 +249,16 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         }
         if constexpr (Meta::MAT) {
           const int bs = P.bs;
+          if (scat) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            // rows owned by the neighbour rank: slot table of ITS matrix (peer memory over NVLink)
-            const long long row = (long long)ra.dof[i] * bs;
-            const long long* ip = row >= P.peer_row0 ? P.peer_rowstart + (row - P.peer_row0) : reinterpret_cast<const long long*>(P.indptr) + row;
-            const long long rs = __ldg(ip);
-            ra.rs[i] = rs;
-            ra.rl[i] = bs == 1 ? 0 : (int)(__ldg(ip + 1) - rs);
+            for (int i = 0; i < N; ++i) {
+              // rows owned by the neighbour rank: slot table of ITS matrix (peer memory over NVLink)
+              const long long row = (long long)ra.dof[i] * bs;
+              const long long* ip = row >= P.peer_row0 ? P.peer_rowstart + (row - P.peer_row0) : reinterpret_cast<const long long*>(P.indptr) + row;
+              const long long rs = __ldg(ip);
+              ra.rs[i] = rs;
+              ra.rl[i] = bs == 1 ? 0 : (int)(__ldg(ip + 1) - rs);
+            }
           }
         }
       }
@@ -313,6 +319,7 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
         const int64_t k0 = stage_of(P, td, num_stages) * CB;  // td: position in the traversal, see stage_of
         const int nent = (int)((P.num_entries - k0) < CB ? (P.num_entries - k0) : CB);
         rc.nent = nent;
+        rc.k0 = k0;
         rc.valid = lane < nent;
         const int64_t k = k0 + (rc.valid ? lane : nent - 1);
         rc.o0 = __ldg(P.offsets + k);
