@@ -555,6 +555,173 @@ def config5_leg(args, rank, world, dev, peak):
 
 
 # ------------------------------------------------------------------------------------------------
+def sample_parity(form, sub, A, nthreads):
+    """`sub` (a host rule on a sample of cells) assembled by the CUDA path into the zeroed full-pattern matrix A against
+    the oracle on the same entries: every (row, column) the oracle produced is looked up in the device CSR (sparsity),
+    values to 1e-12.  A is left holding the sample's contributions."""
+    from customquad_b200 import assemble as asm
+    from oracle import oracle
+
+    V = form.function_spaces[0]
+    asm.assemble_matrix(form, [sub], A=A, zero=True)
+    A.assemble()
+    pat = oracle.build_pattern(V.dofmap.list, V.dofmap.num_dofs, V.bs, cells=sub.cells)
+    R = oracle.assemble_matrix(form, [sub], nthreads=nthreads, pattern=pat).tocoo()
+    keep = R.data != 0.0
+    rr, cc, vv = R.row[keep].astype(np.int64), R.col[keep].astype(np.int64), R.data[keep]
+    rows = np.unique(rr)
+    ip_lo, ip_hi = A.indptr[rows].cpu().numpy(), A.indptr[rows + 1].cpu().numpy()
+    worst, found = 0.0, True
+    scale = float(np.max(np.abs(vv)))
+    order = np.argsort(rr, kind="stable")
+    rr, cc, vv = rr[order], cc[order], vv[order]
+    starts = np.searchsorted(rr, rows)
+    ends = np.append(starts[1:], len(rr))
+    for i in range(0, len(rows), 4096):  # device rows in batches
+        lo, hi = ip_lo[i : i + 4096], ip_hi[i : i + 4096]
+        for j in range(len(lo)):
+            cols = A.indices[int(lo[j]) : int(hi[j])].cpu().numpy() if hi[j] - lo[j] > 4096 else None
+            if cols is None:
+                seg = slice(int(lo[j]), int(hi[j]))
+                cols = A.indices[seg].cpu().numpy()
+            vals = A.data[int(lo[j]) : int(hi[j])].cpu().numpy()
+            a, b = starts[i + j], ends[i + j]
+            pos = np.searchsorted(cols, cc[a:b])
+            ok = (pos < len(cols)) & (cols[np.minimum(pos, len(cols) - 1)] == cc[a:b])
+            found = found and bool(ok.all())
+            if ok.all():
+                worst = max(worst, float(np.max(np.abs(vals[pos] - vv[a:b]))) / scale)
+    return {"entries": int(sub.num_entries), "rows": int(len(rows)), "values": int(len(vv)), "sparsity_ok": found, "max_rel": worst, "ok": bool(found and worst <= RTOL)}
+
+
+def event_ms(fn, reps=5, warm=2):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def config3_leg(dev, peak):
+    """BASELINE.json configs[2]: sphere on Q1 hexahedra 256^3 -- cut-cell volume integrals plus the surface Nitsche terms
+    with quadrature normals, on the rules the device producer generates (cq_sphere_*; demo/poisson.py:100-113 with
+    -domain sphere), and the standard 8-point rule on the uncut cells.  One step: A <- 0; A += stiffness(uncut, 8
+    points); A += stiffness(cut, runtime rule); A += Nitsche(cut, surface rule with normals)."""
+    import torch
+
+    import customquad_b200 as cq
+    from customquad_b200 import assemble as asm
+    from customquad_b200 import forms, levelset
+    from customquad_b200.quadrature import RaggedQuadrature, gauss_tensor_rule
+
+    N3 = int(os.environ.get("CQ_BENCH_C3_N", "256"))
+    mesh = cq.create_box(BOX3, [N3, N3, N3])
+    levelset.generate_qr_sphere_device(cq.create_box([[-1, -1, -1], [1, 1, 1]], [4, 4, 4]), 0.9)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cut, uncut, _outside, qb, qs = levelset.generate_qr_sphere_device(mesh, 1.0, (0.0, 0.0, 0.0), 4)
+    torch.cuda.synchronize()
+    producer_ms = 1e3 * (time.perf_counter() - t0)
+    pts, w = gauss_tensor_rule(3, 2)
+    nq, U = len(w), len(uncut)
+    qu = RaggedQuadrature.on_device(torch.from_numpy(np.ascontiguousarray(uncut, dtype=np.int32)).to(dev), torch.arange(U + 1, dtype=torch.int64, device=dev) * nq,
+                                    torch.from_numpy(pts.reshape(-1)).to(dev).repeat(U), torch.from_numpy(w).to(dev).repeat(U), None, 3)  # fmt: skip
+    V = cq.FunctionSpace(mesh, ("Lagrange", 1))
+    fK, fN = forms.stiffness(V), forms.nitsche(V, 10.0)
+    A = asm.create_matrix(fK)
+    one = forms.integral(mesh, 1.0)
+    vol = float(cq.assemble_scalar(one, [qb])) + float(np.prod(mesh.h())) * U
+    area = float(cq.assemble_scalar(one, [qs]))
+
+    def step():
+        asm.assemble_matrix(fK, [qu], A=A, zero=True)
+        asm.assemble_matrix(fK, [qb], A=A)
+        asm.assemble_matrix(fN, [qs], A=A)
+
+    ms = event_ms(step)
+    ms_k = {"stiffness_uncut_8pt": event_ms(lambda: asm.assemble_matrix(fK, [qu], A=A)), "stiffness_cut": event_ms(lambda: asm.assemble_matrix(fK, [qb], A=A)),
+            "nitsche_cut": event_ms(lambda: asm.assemble_matrix(fN, [qs], A=A)), "zero": event_ms(lambda: A.data.zero_())}  # fmt: skip
+    nodes = mesh.geometry.x.shape[0]
+    ab = (algorithmic_bytes(U, U * nq, 3, 8, 8, nodes, A.nnz) + algorithmic_bytes(qb.num_entries, qb.num_points, 3, 8, 8, 0, 0)
+          + algorithmic_bytes(qs.num_entries, qs.num_points, 3, 8, 8, 0, 0, normals=True))  # fmt: skip
+    T = host_cores()
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(qb.num_entries, min(32768, qb.num_entries), replace=False))
+    par = {"stiffness_cut": sample_parity(fK, qb.select(pick), A, T), "nitsche_cut": sample_parity(fN, qs.select(pick), A, T)}
+    out = {"workload": f"sphere on Q1 hexahedra {N3}^3: 8-point rule on the {U} uncut cells, device-generated cut-cell rules on the {len(cut)} cut cells (volume) + surface rules with normals (Nitsche) (BASELINE.json configs[2])",
+           "cells": int(mesh.num_cells), "cut_cells": int(len(cut)), "bulk_points": int(qb.num_points), "surface_points": int(qs.num_points),
+           "producer_ms": producer_ms, "ms_per_step": ms, "per_kernel_ms": ms_k, "element_tensors_per_s": (U + 2 * len(cut)) / (ms * 1e-3), "csr_nnz_per_s": A.nnz / (ms * 1e-3),
+           "roofline": {"bound": "hbm", "algorithmic_bytes": ab, "achieved_gbs": ab / ms / 1e6, "peak": peak, "frac": ab / ms / 1e6 / peak},
+           "volume_rel_err": abs(vol - 4 * np.pi / 3) / (4 * np.pi / 3), "area_rel_err": abs(area - 4 * np.pi) / (4 * np.pi),
+           "parity": {"checked": True, **{k: v for k, v in par.items()}, "ok": all(v["ok"] for v in par.values()),
+                      "what": "a sample of 32768 cut cells assembled alone by the CUDA path and by the CPU oracle: every value the oracle produced, sparsity by lookup in the device CSR, values to 1e-12"},
+           "parity_pinned_by_reference_tests": "none of these forms (stiffness, Nitsche with normals): sympy closed forms, DESIGN.md 6"}  # fmt: skip
+    del A
+    for q in (qu, qb, qs):
+        q._dev.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def config4_leg(dev, peak):
+    """BASELINE.json configs[3]: demo/vector_poisson.py-style 3-D vector Poisson on Q2 hexahedra 128^3 (bs = 3), the
+    3^3 Gauss rule in every cell as a runtime rule: blocked stiffness matrix (FP64 tensor cores, owner-computes row
+    stores, csrc/cq_owner.cuh) -- 9.69e9 non-zeros, 116 GB of CSR on one GPU.  One step: A <- 0 and A += stiffness in
+    one call (assemble_matrix(form, qr))."""
+    import torch
+
+    import customquad_b200 as cq
+    from customquad_b200 import assemble as asm
+    from customquad_b200 import forms
+    from customquad_b200.quadrature import RaggedQuadrature, gauss_tensor_rule, normalise_qr
+
+    N4 = int(os.environ.get("CQ_BENCH_C4_N", "128"))
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    need = 5.7e4 * N4**3 + 8e9  # CSR + element blocks + rule, measured at 128^3: 133 GB
+    if free_b < need:
+        return {"skipped": f"needs {need / 1e9:.0f} GB of free HBM, {free_b / 1e9:.0f} GB free"}
+    mesh = cq.create_box(BOX3, [N4, N4, N4])
+    V = cq.VectorFunctionSpace(mesh, ("Lagrange", 2))
+    pts, w = gauss_tensor_rule(3, 4)
+    C, nq = mesh.num_cells, len(w)
+    qr = RaggedQuadrature.on_device(torch.arange(C, dtype=torch.int32, device=dev), torch.arange(C + 1, dtype=torch.int64, device=dev) * nq,
+                                    torch.from_numpy(pts.reshape(-1)).to(dev).repeat(C), torch.from_numpy(w).to(dev).repeat(C), None, 3)  # fmt: skip
+    fK = forms.stiffness(V)
+    K = asm.create_matrix(fK, zero=False)
+    ms = event_ms(lambda: asm.assemble_matrix(fK, [qr], A=K, zero=True), reps=3, warm=1)
+    K.assemble()
+    chunks = [K.data[i : i + (1 << 28)] for i in range(0, K.nnz, 1 << 28)]  # no full-size temporaries
+    total_rel = abs(sum(float(c.sum()) for c in chunks)) / sum(float(c.abs().sum()) for c in chunks)  # 1^T K 1 = 0 (rigid translations)
+    ab = algorithmic_bytes(C, C * nq, 3, 8, 27, mesh.geometry.x.shape[0], K.nnz)
+    flops = 2.0 * 3 * 27 * 27 * C * nq  # B^T D B over the three gradient components
+    _dfma, dmma, _ = measured_fp64()
+    t_hbm, t_f64 = ab / (peak * 1e6), flops / (dmma * 1e9)
+    pick = np.sort(np.random.default_rng(2).choice(C, 2048, replace=False))
+    sub = normalise_qr((pick, np.tile(pts.reshape(-1), [len(pick), 1]), np.tile(w, [len(pick), 1])), 3)
+    par = sample_parity(fK, sub, K, host_cores())
+    out = {"workload": f"vector Poisson stiffness, Q2 hexahedra {N4}^3, bs = 3, {nq} points per cell (BASELINE.json configs[3])", "cells": int(C), "dofs": int(V.num_dofs),
+           "nnz": int(K.nnz), "csr_GB": K.nnz * 12 / 1e9, "ms_per_step": ms, "element_tensors_per_s": C / (ms * 1e-3), "csr_nnz_per_s": K.nnz / (ms * 1e-3),
+           "path": "owner-computes (cq_owner.cuh): element blocks by the tensor-core kernel, every blocked row stored once, zeroEntries fused",
+           "roofline": {"bound": "hbm" if t_hbm >= t_f64 else "fp64", "algorithmic_bytes": ab, "algorithmic_flops": flops, "achieved_gbs": ab / ms / 1e6, "peak": peak,
+                        "frac": ab / ms / 1e6 / peak, "frac_fp64_dmma": t_f64 / ms},
+           "sum_of_all_entries_rel": total_rel,
+           "parity": {"checked": True, **par, "what": "2048 random cells assembled alone by the CUDA path (same kernels) and by the CPU oracle: every value the oracle produced, values to 1e-12"},
+           "parity_pinned_by_reference_tests": "none (the reference's Q2 tests are xfail): sympy closed forms and the convergence of examples/vector_poisson.py, DESIGN.md 6"}  # fmt: skip
+    del K, chunks
+    qr._dev.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
 def general_cells_leg(dev, peak):
     """The headline workload on a DISTORTED mesh: no cell is axis-aligned, cq_mesh_classify says so, and the same four
     assemble_matrix calls run the point-by-point staged kernels (MODE 0) instead of the moment kernels."""
@@ -850,6 +1017,12 @@ def run_gpu(args):
             extra["list_input"] = list_input_leg(qr)
             qr._dev.clear()
             extra["general_cells"] = general_cells_leg(dev, peak)
+            if os.environ.get("CQ_BENCH_C3", "1") != "0":
+                log("extra: config 3 (sphere, Q1 hexahedra 256^3)")
+                extra["config3"] = config3_leg(dev, peak)
+            if os.environ.get("CQ_BENCH_C4", "1") != "0":
+                log("extra: config 4 (vector Poisson, Q2 hexahedra 128^3)")
+                extra["config4"] = config4_leg(dev, peak)
         except Exception as e:  # noqa: BLE001
             import traceback
 
@@ -872,12 +1045,12 @@ def run_gpu(args):
     # flush before any teardown: stdout is block-buffered when redirected, and a line lost to a late
     # failure (seen once: an empty output file from a 4-GPU run whose timed region had finished) is a lost run
     emit(line)
-    bad = (parity is not None and not parity["ok"]) or (isinstance(extra.get("config5"), dict) and extra["config5"].get("parity", {}).get("ok") is False)
+    bad = (parity is not None and not parity["ok"]) or any(isinstance(extra.get(k), dict) and extra[k].get("parity", {}).get("ok") is False for k in ("config3", "config4", "config5"))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if bad:
-        log("PARITY FAILURE at the partition interfaces")
+        log("PARITY FAILURE (partition interfaces or an extra config)")
         sys.exit(3)
 
 

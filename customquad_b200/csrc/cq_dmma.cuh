@@ -35,24 +35,28 @@ CQ_DEVINL void dmma_m8n8k4(double (&d)[2], const double a, const double b) {
 // run-time selects: the compiler turned those into divergent branches and local-memory traffic, and the eight lanes
 // that share a point repeated its basis and Jacobian (measured 0.37 of the DMMA peak; the tensor core waited on
 // scalar code).  Now the warp first fills a TABLE in shared memory, one row per point, one lane per point:
-//   [0..8]   l_a(xi_d) at d * 3 + a      [9]  0.0   (the padding dofs 27..31 read the zeros)
-//   [10..18] l_a'(xi_d) at 10 + d * 3 + a [19] 0.0
-//   [20..]   the point's factors: stiffness G = w / |det J| adj adj^T (6 values), mass w |det J|,
-//            Nitsche w |det J|, w |det J| gamma, m = adj n / det J
+//   [2 i, 2 i + 1]  the pair (l_a(xi_d), l_a'(xi_d)), i = d * 3 + a: one 16-byte load per factor
+//   [18, 19]        (0, 0): the padding dofs 27..31 read these
+//   [20..]          the point's factors: stiffness G = w / |det J| adj adj^T (6 values), mass w |det J|,
+//                   Nitsche w |det J|, w |det J| gamma, m = adj n / det J
 // and the k-steps read each lane's factors through per-lane row offsets fixed for the whole kernel.  The table lives
-// in the warp's 27 x 28 scatter tile (28 rows of 27 doubles: a 27-point rule is one chunk).
+// in the warp's 27 x 28 scatter tile (28 rows of 26 doubles: a 27-point rule is one chunk).  Row stride 26 doubles =
+// 13 sixteen-byte units: the four rows a load instruction touches (points 4 s + t) put their three pairs on bank
+// groups {0,1,2} {5,6,7} {2,3,4} {7,0,1} -- at most two per group, the minimum for twelve 16-byte words (the first
+// layout, separate value / derivative arrays at stride 27, measured 3-4 wavefronts per 8-byte load: the shared-memory
+// pipe, not the tensor core, was the busiest unit, profiles/r2s2/ncu_q2hex_phase1_stride27.txt).
 // Stiffness: S_ij = sum_q g_i^T G g_j with g the REFERENCE gradient: the A fragment is g itself, the B fragment G g.
-constexpr int DT_STRIDE = 27;  // doubles per table row
-constexpr int DT_POINTS = 28;  // rows: 28 * 27 = 27 * 28 doubles, the scatter tile
+constexpr int DT_STRIDE = 26;  // doubles per table row
+constexpr int DT_POINTS = 28;  // rows: 28 * 26 <= 27 * 28 doubles, the scatter tile
 
-// this lane's row offsets: dof 8 * tile + g, factor of dimension d
+// this lane's row offsets (in doubles, even): dof 8 * tile + g, factor of dimension d
 CQ_DEVINL void dmma_lane_offsets(const int g, int (&off)[4][3]) {
 #pragma unroll
   for (int tile = 0; tile < 4; ++tile) {
     const int j = 8 * tile + g;
     const int pk = c_q2hex_lat[j];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) off[tile][d] = j < 27 ? d * 3 + ((pk >> (2 * d)) & 3) : 9;
+    for (int d = 0; d < 3; ++d) off[tile][d] = 2 * (j < 27 ? d * 3 + ((pk >> (2 * d)) & 3) : 9);
   }
 }
 
@@ -76,13 +80,9 @@ CQ_DEVINL void dmma_fill_table(double* __restrict__ tab, const CellGeom<3>& geo,
     for (int d = 0; d < 3; ++d) {
       const Basis1D<2> b(xi[d]);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        row[d * 3 + a] = b.v[a];
-        row[10 + d * 3 + a] = b.d[a];
-      }
+      for (int a = 0; a < 3; ++a) *reinterpret_cast<double2*>(row + 2 * (d * 3 + a)) = make_double2(b.v[a], b.d[a]);
     }
-    row[9] = 0.0;
-    row[19] = 0.0;
+    *reinterpret_cast<double2*>(row + 18) = make_double2(0.0, 0.0);
     double adj[3][3], det;
     if (geo.affine) {  // constant Jacobian: per-cell values
       det = geo.det0;
@@ -127,7 +127,7 @@ CQ_DEVINL void dmma_table_steps(double (&D)[10][2], const double* __restrict__ t
       double f[4], sf[4];
 #pragma unroll
       for (int tile = 0; tile < 4; ++tile) {
-        f[tile] = row[off[tile][0]] * row[off[tile][1]] * row[off[tile][2]];
+        f[tile] = row[off[tile][0]] * row[off[tile][1]] * row[off[tile][2]];  // the values of the pairs
         sf[tile] = s * f[tile];
       }
       int e = 0;
@@ -139,11 +139,12 @@ CQ_DEVINL void dmma_table_steps(double (&D)[10][2], const double* __restrict__ t
       double gr[4][3];
 #pragma unroll
       for (int tile = 0; tile < 4; ++tile) {
-        const double v0 = row[off[tile][0]], v1 = row[off[tile][1]], v2 = row[off[tile][2]];
-        const double d0 = row[off[tile][0] + 10], d1 = row[off[tile][1] + 10], d2 = row[off[tile][2] + 10];
-        gr[tile][0] = d0 * (v1 * v2);
-        gr[tile][1] = (v0 * v2) * d1;
-        gr[tile][2] = (v0 * v1) * d2;
+        const double2 p0 = *reinterpret_cast<const double2*>(row + off[tile][0]);  // (value, derivative)
+        const double2 p1 = *reinterpret_cast<const double2*>(row + off[tile][1]);
+        const double2 p2 = *reinterpret_cast<const double2*>(row + off[tile][2]);
+        gr[tile][0] = p0.y * (p1.x * p2.x);
+        gr[tile][1] = (p0.x * p2.x) * p1.y;
+        gr[tile][2] = (p0.x * p1.x) * p2.y;
       }
       const double G00 = row[20], G11 = row[23], G22 = row[25];
       if (diagG) {  // axis-aligned cell (every cell of a create_box mesh): G is diagonal
@@ -179,11 +180,12 @@ CQ_DEVINL void dmma_table_steps(double (&D)[10][2], const double* __restrict__ t
       double psi[4], ev[4], uv[4];
 #pragma unroll
       for (int tile = 0; tile < 4; ++tile) {
-        const double v0 = row[off[tile][0]], v1 = row[off[tile][1]], v2 = row[off[tile][2]];
-        const double d0 = row[off[tile][0] + 10], d1 = row[off[tile][1] + 10], d2 = row[off[tile][2] + 10];
-        const double v12 = v1 * v2;
-        const double dn = fma(m2, (v0 * v1) * d2, fma(m1, (v0 * v2) * d1, m0 * (d0 * v12)));
-        psi[tile] = v0 * v12;
+        const double2 p0 = *reinterpret_cast<const double2*>(row + off[tile][0]);  // (value, derivative)
+        const double2 p1 = *reinterpret_cast<const double2*>(row + off[tile][1]);
+        const double2 p2 = *reinterpret_cast<const double2*>(row + off[tile][2]);
+        const double v12 = p1.x * p2.x;
+        const double dn = fma(m2, (p0.x * p1.x) * p2.y, fma(m1, (p0.x * p2.x) * p1.y, m0 * (p0.y * v12)));
+        psi[tile] = p0.x * v12;
         ev[tile] = s * dn;
         uv[tile] = fma(sg, psi[tile], -ev[tile]);
       }
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(THREADS) assemble_q2hex_dmma_kernel(const KPar
 
   int off[4][3];
   dmma_lane_offsets(g, off);
-  __shared__ double tab_all[THREADS / 32][DT_POINTS * DT_STRIDE];
+  __shared__ __align__(16) double tab_all[THREADS / 32][DT_POINTS * DT_STRIDE];
   double* tab = tab_all[threadIdx.x >> 5];
 
   for (int64_t k = warp_id; k < P.num_entries; k += num_warps) {

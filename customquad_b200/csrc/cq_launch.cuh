@@ -245,6 +245,9 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NMW3
 #define CQ_MOMENT_NMW3 4
 #endif
+#ifndef CQ_MOMENT_NPP3   // producer warps per stage slot, Q1 hexahedra
+#define CQ_MOMENT_NPP3 1
+#endif
 #ifndef CQ_MOMENT_NXS3
 #define CQ_MOMENT_NXS3 2
 #endif
@@ -305,8 +308,8 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // rate, not by bytes -> six slots (measured on 128^3 cells, 8 points: stiffness 0.513 -> 0.475 ms, mass
         // 0.491 -> 0.466 ms; with U{8..27} points six slots no longer hold a stage and cost 0.60 -> 0.80 ms)
         if (P.num_points <= 12 * P.num_entries)
-          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
-        return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true>(ctx, P, s);
+          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
+        return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
       }
     }
     return launch_staged<T, S::G, S::NPW, S::NCW>(ctx, P, s);

@@ -31,7 +31,7 @@ struct OwnerParams {
   int64_t num_dofs;
   int n;     // scalar dofs per cell
   int npos;  // scatter-map stride
-  int bs;
+  int bs;  // 2 or 3 here
   int overwrite;  // 1: store (zero_first), 0: add
   const int32_t* __restrict__ cells;
   const int32_t* __restrict__ dofmap;
@@ -40,7 +40,7 @@ struct OwnerParams {
   double* values;
   int* cnt;                        // [num_dofs + 1]
   unsigned int* ptr;               // [num_dofs + 1]
-  int2* pairs;                     // [num_entries * n]: (k, li)
+  int2* pairs;                     // [num_entries * n]: (k * 32 + li, cell), grouped by dof
   const double* __restrict__ elem; // [num_entries, n * n]
 };
 
@@ -60,62 +60,82 @@ __global__ void owner_fill_kernel(const OwnerParams O) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t k = idx / O.n;
     const int li = (int)(idx - k * O.n);
-    const int32_t dof = __ldg(O.dofmap + (int64_t)__ldg(O.cells + k) * O.n + li);
+    const int32_t cell = __ldg(O.cells + k);
+    const int32_t dof = __ldg(O.dofmap + (int64_t)cell * O.n + li);
     const int slot = atomicSub(O.cnt + dof, 1) - 1;
-    O.pairs[(int64_t)O.ptr[dof] + slot] = make_int2((int)k, li);
+    O.pairs[(int64_t)O.ptr[dof] + slot] = make_int2((int)k * 32 + li, cell);  // n <= 32, num_entries * n < 2^31
   }
 }
 
 constexpr int OWNER_WARPS = 8;
 constexpr int OWNER_ROW_MAX = 256;  // scatter positions are bytes: a scalar row holds at most 256 couplings
 
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(OWNER_WARPS * 32) owner_rows_kernel(const OwnerParams O) {
+// BS: the block size as a compile-time constant (the slot -> (coupling, component) split of the store loop is a
+// division per stored double: with a run-time divisor the kernel was bound by its instruction count, 23 ms for the
+// 77.5 GB of config 4 instead of the ~13 ms the stores take)
+template <int BS_T>  // 0: run-time block size
+__global__ void __launch_bounds__(OWNER_WARPS * 32, 8) owner_rows_kernel(const OwnerParams O) {
+  const int BS = BS_T > 0 ? BS_T : O.bs;
   __shared__ double buf_all[OWNER_WARPS][OWNER_ROW_MAX];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* __restrict__ buf = buf_all[wib];
-  const int n = O.n, nn = O.n * O.n, bs = O.bs;
+  const int n = O.n, nn = O.n * O.n;
   const int64_t nwarps = (int64_t)gridDim.x * OWNER_WARPS;
   for (int64_t d = (int64_t)blockIdx.x * OWNER_WARPS + wib; d < O.num_dofs; d += nwarps) {
     const unsigned int p0 = __ldg(O.ptr + d), p1 = __ldg(O.ptr + d + 1);
     if (p0 == p1 && !O.overwrite) continue;
-    const int64_t r0 = __ldg(O.indptr + d * bs);
-    const int len_b = (int)(__ldg(O.indptr + d * bs + 1) - r0);  // blocked row length (the bs rows of a dof are equally long)
-    const int len = len_b / bs;
+    const int64_t r0 = __ldg(O.indptr + d * BS);
+    const int len_b = (int)(__ldg(O.indptr + d * BS + 1) - r0);  // blocked row length (the BS rows of a dof are equally long and contiguous)
+    const int len = len_b / BS;
     for (int p = lane; p < len; p += 32) buf[p] = 0.0;
     __syncwarp();
     for (unsigned int c0 = p0; c0 < p1; c0 += 32) {
       const int m = (int)(p1 - c0 < 32u ? p1 - c0 : 32u);
       int2 pr = make_int2(0x7fffffff, 0);
-      int32_t cell = 0;
-      if (lane < m) {
-        pr = O.pairs[c0 + lane];
-        cell = __ldg(O.cells + pr.x);
-      }
+      if (lane < m) pr = O.pairs[c0 + lane];
       int key = pr.x;
-      for (int it = 0; it < m; ++it) {  // ascending list position: a fixed summation order
-        const int kmin = __reduce_min_sync(0xffffffffu, key);
-        const int src = __ffs(__ballot_sync(0xffffffffu, key == kmin)) - 1;
-        const int li = __shfl_sync(0xffffffffu, pr.y, src);
-        const int32_t cl = __shfl_sync(0xffffffffu, cell, src);
-        if (lane == src) key = 0x7fffffff;
-        if (lane < n) {
-          const double v = __ldg(O.elem + (int64_t)kmin * nn + li * n + lane);
-          const unsigned pos = __ldg(O.elem_pos + (int64_t)cl * O.npos + li * n + lane);
-          buf[pos] += v;
+      // ascending list position: a fixed summation order.  U entries at a time: their loads are all in flight before
+      // the first add (the adds of one entry hit distinct slots; consecutive entries are ordered by the warp barrier)
+      constexpr int U = 4;
+      for (int it = 0; it < m; it += U) {
+        double v[U];
+        unsigned pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int kmin = __reduce_min_sync(0xffffffffu, key);  // 0x7fffffff once the chunk is exhausted
+          const int src = __ffs(__ballot_sync(0xffffffffu, key == kmin)) - 1;
+          const int32_t cl = __shfl_sync(0xffffffffu, pr.y, src);
+          if (lane == src) key = 0x7fffffff;
+          const int li = kmin & 31;
+          v[u] = 0.0;
+          pos[u] = 0;
+          if (it + u < m && lane < n) {
+            v[u] = __ldg(O.elem + (int64_t)(kmin >> 5) * nn + li * n + lane);
+            pos[u] = __ldg(O.elem_pos + (int64_t)cl * O.npos + li * n + lane);
+          }
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (it + u < m && lane < n) buf[pos[u]] += v[u];
+          __syncwarp();
+        }
       }
     }
-    for (int a = 0; a < bs; ++a) {
-      double* __restrict__ row = O.values + __ldg(O.indptr + d * bs + a);
+    // row a of the dof (the BS rows are contiguous and equally long): slot idx = p * BS + b holds buf[p] iff b == a
+#pragma unroll
+    for (int a = 0; a < (BS_T > 0 ? BS_T : BS); ++a) {
+      double* __restrict__ row = O.values + r0 + (int64_t)a * len_b;
       if (O.overwrite) {
+#pragma unroll 4
         for (int idx = lane; idx < len_b; idx += 32) {
-          const int p = idx / bs;
-          row[idx] = (idx - p * bs == a) ? buf[p] : 0.0;
+          const int p = idx / BS;
+          row[idx] = (idx - p * BS == a) ? buf[p] : 0.0;
         }
       } else {
-        for (int p = lane; p < len; p += 32) row[p * bs + a] += buf[p];
+        for (int idx = lane; idx < len_b; idx += 32) {
+          const int p = idx / BS;
+          if (idx - p * BS == a) row[idx] += buf[p];
+        }
       }
     }
     __syncwarp();

@@ -207,18 +207,21 @@ CQ_DEVINL void staged_producer(const KParams& P, unsigned char* base, uint64_t* 
             for (int i = 0; i < T::NCOEF; ++i) M.coef[i][lane] = __ldg(c + i);
           }
         }
-        // sort entries by trip count, longest first (bitonic over the 32 lanes)
+        // sort entries by trip count, longest first (bitonic over the 32 lanes); nothing to sort when every entry has
+        // the same number of points (a standard rule tiled over the cells: the bulk of configs 4 and 5)
         int key = (((nq + G - 1) / G) << 5) | (31 - lane);  // ties: lower lane first
+        if (!__all_sync(0xffffffffu, nq == __shfl_sync(0xffffffffu, nq, 0))) {
 #pragma unroll
-        for (int size = 2; size <= 32; size <<= 1)
+          for (int size = 2; size <= 32; size <<= 1)
 #pragma unroll
-          for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-            const int other = __shfl_xor_sync(0xffffffffu, key, stride);
-            const bool desc = (lane & size) == 0;
-            const bool lower = (lane & stride) == 0;
-            const int mx = key > other ? key : other, mn = key > other ? other : key;
-            key = (desc == lower) ? mx : mn;
-          }
+            for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+              const int other = __shfl_xor_sync(0xffffffffu, key, stride);
+              const bool desc = (lane & size) == 0;
+              const bool lower = (lane & stride) == 0;
+              const int mx = key > other ? key : other, mn = key > other ? other : key;
+              key = (desc == lower) ? mx : mn;
+            }
+        }
         M.order[lane] = 31 - (key & 31);
         if (lane == 0) {
           M.nent = nent;

@@ -19,14 +19,16 @@ shape, N, degree, kind, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 5
 tdim = 2 if shape == "quad" else 3
 mesh = cq.create_rectangle([[-1.11, -1.51], [1.55, 1.22]], [N, N]) if tdim == 2 else cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [N, N, N])
-V = cq.FunctionSpace(mesh, ("Lagrange", degree))
+BS = int(os.environ.get("CQ_BS", "1"))  # block size of the space
+ZERO = os.environ.get("CQ_ZERO", "0") == "1"  # matrices: A.zeroEntries() as part of the call
+V = cq.FunctionSpace(mesh, ("Lagrange", degree), BS) if BS > 1 else cq.FunctionSpace(mesh, ("Lagrange", degree))
 qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), tdim, lo, hi, seed=5, normals=True)
 dev = torch.device("cuda", 0)
 asm.qr_on_device(qr, dev)
 if kind in ("mass", "stiffness", "nitsche"):
     form = forms.nitsche(V, 10.0) if kind == "nitsche" else getattr(forms, kind)(V)
     A = asm.create_matrix(form)
-    fn = lambda: asm.assemble_matrix(form, [qr], A=A)  # noqa: E731
+    fn = lambda: asm.assemble_matrix(form, [qr], A=A, zero=ZERO)  # noqa: E731
     out = 8 * A.nnz
 elif kind in ("load", "load_coef", "nitsche_rhs"):
     if kind == "load":
