@@ -1080,7 +1080,17 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (N=1: general cells, list input; N>1: config 5, also CQ_BENCH_C5=0)")
     ap.add_argument("--fused-zero", action="store_true", help="zero the matrices inside the moment kernels (cq_ctx_set_fused_zero)")
     ap.add_argument("--forms", default="", help="development only: comma-separated subset of the workload's forms (changes the workload; shown in config.forms)")
+    ap.add_argument("--only-config", type=int, default=0, choices=[0, 3, 4], help="run just the extra leg of BASELINE.json configs[N-1] on one GPU and print its JSON (tests/test_gpu_full_size.py; not the contract line)")
     args = ap.parse_args()
+    if args.only_config:
+        import torch
+
+        torch.cuda.set_device(0)
+        dev = torch.device("cuda", 0)
+        peak, _ = measured_peak()
+        out = (config3_leg if args.only_config == 3 else config4_leg)(dev, peak)
+        emit({"only_config": args.only_config, **out})
+        sys.exit(0 if out.get("skipped") or out["parity"]["ok"] else 3)
     if args.forms:
         global FORMS
         FORMS = [f for f in FORMS if f[0] in args.forms.split(",")]

@@ -32,7 +32,7 @@ template <class TQ2, int NPW>
 static int launch_owner_q2hex(cq_ctx* ctx, const KParams& P, cudaStream_t s, bool* done) {
   *done = false;
   constexpr int N = TQ2::N;
-  if (P.bs < 2 || P.bs > 3 || P.peer_rowstart != nullptr || ctx->variant != 0 || P.num_dofs <= 0) return CQ_OK;
+  if (!P.zero_req || P.bs < 2 || P.bs > 3 || P.peer_rowstart != nullptr || ctx->variant != 0 || P.num_dofs <= 0) return CQ_OK;
   if (P.num_entries >= (1LL << 26) || P.num_dofs >= 0x7fffffffLL) return CQ_OK;  // (k * 32 + li) and the pair offsets are 32-bit
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t nd1 = (size_t)P.num_dofs + 1;
@@ -54,7 +54,7 @@ static int launch_owner_q2hex(cq_ctx* ctx, const KParams& P, cudaStream_t s, boo
   unsigned char* w = static_cast<unsigned char*>(ctx->owner_ws);
   if (int rc = check_cuda(cudaMemsetAsync(w, 0, b_cnt, s), "memset(owner counts)")) return rc;
   OwnerParams O;
-  O.num_entries = P.num_entries; O.num_dofs = P.num_dofs; O.n = N; O.npos = StageMeta<TQ2, 32>::NPOS; O.bs = P.bs; O.overwrite = P.zero_req;
+  O.num_entries = P.num_entries; O.num_dofs = P.num_dofs; O.n = N; O.npos = StageMeta<TQ2, 32>::NPOS; O.bs = P.bs;
   O.cells = P.cells; O.dofmap = P.dofmap; O.elem_pos = P.elem_pos; O.indptr = P.indptr; O.values = P.values;
   O.cnt = reinterpret_cast<int*>(w);
   O.ptr = reinterpret_cast<unsigned int*>(w + b_cnt);

@@ -193,8 +193,16 @@ CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const 
   const int nq = active ? M.nq[e] : 0;
   const double* pp = M.pts[e];
   const double* wp = M.w[e];
+  // Every entry starts its point loop at a different point (the sum is over all of them anyway).  With the fixed
+  // 8-point rule of the uncut cells the entries lie 192 bytes apart in the stage: un-rotated, the sixteen entries of
+  // a load instruction hit two bank groups (ncu: 8 wavefronts per cell for the point loads, ideal 2,
+  // profiles/r2/ncu_src_hexq1_stiffness_8pt_before.txt); rotated by e / 2 they tile all 32 banks twice.
+  int rot = 0;
+  if (nq > 1) rot = (e >> 1) & ((1 << (31 - __clz(nq))) - 1);
 #pragma unroll 2
-  for (int q = r; q < nq; q += G) {
+  for (int q0 = r; q0 < nq; q0 += G) {
+    int q = q0 + rot;
+    if (q >= nq) q -= nq;
     const double t0 = pp[3 * q] - 0.5, t1 = pp[3 * q + 1] - 0.5, t2 = pp[3 * q + 2] - 0.5;
     const double w = wp[q];
     double Z[Pn], YZ[Pn][Pn];

@@ -3,6 +3,8 @@ size-independent properties + the oracle on a fixed random sample of >= 65,536 c
 same sparsity).  Properties used: constants are in the kernel of the stiffness matrix (row sums 0), the
 mass matrix integrates 1 (sum of entries = sum_c |K_c| sum_q w_q), symmetry (x'Ay = y'Ax), linearity
 in the weights, and for scalars sum w = measure."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +16,7 @@ from customquad_b200.quadrature import synthetic_ragged
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
 def _row_sums(A):
@@ -198,3 +201,35 @@ def test_long_list_takes_the_ticket_path(cuda_backend):
             assert np.max(np.abs(got_v - ref.data)) <= RTOL * np.max(np.abs(ref.data))
     b = cq.assemble_vector(forms.load(V, 1.0), [qr]).array  # the vector kernels share the producer
     assert abs(b.sum() - cell_vol * qr.w.sum()) <= RTOL * abs(b.sum())
+
+
+def _bench_leg(config, timeout=900):
+    """One extra leg of bench.py in a process of its own (its allocations: config 4 holds 133 GB)."""
+    import json
+    import subprocess
+    import sys
+
+    torch.cuda.empty_cache()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--only-config", str(config)], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_config3_full_size_256_on_device_rules(cuda_backend):
+    """BASELINE.json configs[2] at its full size: sphere on Q1 hexahedra 256^3, rules from the device producer; volume
+    and area of the unit sphere, and a 32768-cut-cell sample of the stiffness and Nitsche matrices against the oracle."""
+    d = _bench_leg(3)
+    assert d["cells"] == 256**3 and d["cut_cells"] > 150000
+    assert d["volume_rel_err"] < 1e-8 and d["area_rel_err"] < 1e-6
+    assert d["parity"]["ok"] and d["parity"]["stiffness_cut"]["sparsity_ok"] and d["parity"]["nitsche_cut"]["max_rel"] <= RTOL
+
+
+def test_config4_full_size_128_q2_vector(cuda_backend):
+    """BASELINE.json configs[3] at its full size: vector Poisson on Q2 hexahedra 128^3 (9.69e9 non-zeros, 116 GB of CSR).
+    The sum of all entries of the stiffness matrix vanishes, a 2048-cell sample matches the oracle to 1e-12."""
+    d = _bench_leg(4)
+    if d.get("skipped"):
+        pytest.skip(d["skipped"])
+    assert d["nnz"] == 9692015625
+    assert d["sum_of_all_entries_rel"] < 1e-13
+    assert d["parity"]["ok"] and d["parity"]["sparsity_ok"] and d["parity"]["max_rel"] <= RTOL
