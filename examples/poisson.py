@@ -46,6 +46,31 @@ def solve(N, betaN=10.0, betas=1.0, order=4, domain="circle", qr="host"):
             rules = (cut, uncut, outside, None, np.split(qb.host().w, qb.host().offsets[1:-1]), None, np.split(qs.host().w, qs.host().offsets[1:-1]), None)
         else:
             rules = generate_qr_circle(mesh, 1.0, (0.0, 0.0), order)
+    elif domain in ("square", "flower"):
+        # the reference's third level set (demo/square.hpp) and a smooth non-convex one given as callables: rules from
+        # customquad_b200/levelset_general.py (host), the same hot path behind them
+        from customquad_b200.levelset_general import generate_qr_box, generate_qr_levelset
+
+        assert qr == "host", "device producers: circle and sphere"
+        xmin, xmax = np.array([-1.11, -1.51]), np.array([1.55, 1.22])
+        mesh = cq.create_rectangle([xmin, xmax], [N, N])
+        if domain == "square":
+            volume_exact, area_exact = 4.0, 8.0
+            rules = generate_qr_box(mesh, order=order)
+        else:
+            th = np.linspace(0, 2 * np.pi, 400001)
+            volume_exact = np.pi * (0.8**2 + 0.15**2 / 2)
+            area_exact = float(np.trapezoid(np.sqrt((0.8 + 0.15 * np.cos(5 * th)) ** 2 + (0.75 * np.sin(5 * th)) ** 2), th))
+
+            def phi(x):
+                return np.hypot(x[:, 0], x[:, 1]) - (0.8 + 0.15 * np.cos(5 * np.arctan2(x[:, 1], x[:, 0])))
+
+            def grad(x):
+                r, t = np.hypot(x[:, 0], x[:, 1]), np.arctan2(x[:, 1], x[:, 0])
+                dr = 0.75 * np.sin(5 * t)
+                return np.stack([x[:, 0] / r - dr * x[:, 1] / r**2, x[:, 1] / r + dr * x[:, 0] / r**2], axis=1)
+
+            rules = generate_qr_levelset(mesh, phi, grad, order=order)
     else:
         xmin, xmax = np.array([-1.11, -1.51, -1.23]), np.array([1.55, 1.22, 1.11])
         volume_exact, area_exact = 4 * np.pi / 3, 4 * np.pi
@@ -113,7 +138,7 @@ if __name__ == "__main__":
     ap.add_argument("-N", type=int, default=32)  # demo/poisson.py:13
     ap.add_argument("-betaN", type=float, default=10.0)
     ap.add_argument("-betas", type=float, default=1.0)
-    ap.add_argument("-domain", default="circle", choices=["circle", "sphere"])  # demo/poisson.py:17
+    ap.add_argument("-domain", default="circle", choices=["circle", "sphere", "square", "flower"])  # demo/poisson.py:17 (+ demo/square.hpp, a smooth callable level set)
     ap.add_argument("-qr", default="host", choices=["host", "device"], help="where the cut-cell rules are produced")
     a = ap.parse_args()
     print(json.dumps(solve(a.N, a.betaN, a.betas, domain=a.domain, qr=a.qr)))
