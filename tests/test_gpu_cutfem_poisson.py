@@ -115,11 +115,11 @@ def test_poisson_square_and_flower_converge(cuda_backend):
     callables (customquad_b200/levelset_general.py) through the same CUDA assembly path."""
     import poisson
 
-    for domain, vol_tol in (("square", 1e-12), ("flower", 1e-6)):
+    for domain, tol_coarse, tol_fine in (("square", 1e-12, 1e-12), ("flower", 2e-4, 1e-6)):  # flower: 1.2e-4 at N = 16, 4e-8 at N = 64
         res = [poisson.solve(N, domain=domain) for N in (16, 32, 64)]
         for r in res:
-            assert r["functional_area_err"] < max(vol_tol, 2e-5 if domain == "flower" else 0.0), (domain, r)
-            assert r["functional_volume_err"] < max(vol_tol, 2e-5 if domain == "flower" else 0.0), (domain, r)
+            tol = tol_fine if r["N"] == 64 else tol_coarse
+            assert r["functional_area_err"] < tol and r["functional_volume_err"] < tol, (domain, r)
             assert abs(r["functional_volume_err"] - r["qr_volume_err"]) < 1e-11
         l2 = [r["L2_err"] for r in res]
         h1 = [r["H10_err"] for r in res]
