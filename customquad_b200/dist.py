@@ -75,6 +75,16 @@ def make_slab(points, n, rank: int, world: int, bounds=None) -> Slab:
     nn = list(n)
     nn[axis] = last - lo
     mesh = (create_rectangle if tdim == 2 else create_box)(q, nn)
+    # The slab's vertices carry the GLOBAL mesh's coordinates bit for bit (same expression as create_rectangle /
+    # create_box with the global index).  Generated from the slab's own corner they differ from the neighbour's copy
+    # of the same vertices by an ulp, i.e. by eps * |x| / h relative in the cell width: 3e-12 on the interface rows of
+    # the 8-GPU weak-scaling mesh (x ~ 20, h = 1.3e-3), seen by the in-bench parity check.
+    gx = p[0, axis] + (p[1, axis] - p[0, axis]) * (np.arange(lo, last + 1) / n[axis])
+    if tdim == 2:
+        mesh.geometry.x[:, 0] = np.repeat(gx, nn[1] + 1)  # vertex id = ix * (ny + 1) + iy
+    else:
+        mesh.geometry.x.reshape(nn[2] + 1, nn[1] + 1, nn[0] + 1, 3)[..., 2] = gx[:, None, None]  # vertex id = (iz * nvy + iy) * nvx + ix
+    mesh.xmin[axis], mesh.xmax[axis] = gx[0], gx[-1]
     per_layer = mesh.num_cells // nn[axis]
     cells = np.arange(ghost * per_layer, mesh.num_cells, dtype=np.int32)  # layers are the slowest cell index
     return Slab(mesh, cells, first, last - first, ghost, rank, world)

@@ -205,9 +205,11 @@ def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
     assert mesh_on_device(dist, torch.device("cuda", torch.cuda.current_device()))[2] == 0
 
 
+@pytest.mark.parametrize("nq_lo,nq_hi", [(0, 40), (40, 200)], ids=["short", "long-rules-two-slots"])
 @pytest.mark.parametrize("bs", [1, 3])
-def test_moment_kernel_hexahedra(cuda_backend, oracle_backend, bs):
-    """Axis-aligned Q1 hexahedra (create_box) take the 27-moment kernel for mass / stiffness."""
+def test_moment_kernel_hexahedra(cuda_backend, oracle_backend, bs, nq_lo, nq_hi):
+    """Axis-aligned Q1 hexahedra (create_box) take the 27-moment kernel for mass / stiffness; rules of more than 36
+    points per cell on average (real cut cells: config 3) its two-slot variant (cq_launch.cuh:CQ_MOMENT_LONG3)."""
     from customquad_b200.assemble import mesh_on_device, set_variant
     import torch
 
@@ -216,7 +218,7 @@ def test_moment_kernel_hexahedra(cuda_backend, oracle_backend, bs):
     V = cq.FunctionSpace(mesh, ("Lagrange", 1)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", 1))
     rng = np.random.default_rng(37)
     cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 40), np.arange(mesh.num_cells)])
-    qr = synthetic_ragged(cells, 3, 0, 40, seed=17, normals=True)
+    qr = synthetic_ragged(cells, 3, nq_lo, nq_hi, seed=17, normals=True)
     for form in (forms.mass(V), forms.stiffness(V), forms.nitsche(V, 10.0)):
         R = oracle_backend.matrix(form, [qr])
         set_variant(0)
