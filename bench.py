@@ -42,6 +42,8 @@ sys.path.insert(0, ROOT)
 MESH_N = 2048
 NQ_LO, NQ_HI = 16, 64
 XMIN, XMAX = [-1.11, -1.51], [1.55, 1.22]  # demo/poisson.py:42-43
+if os.environ.get("CQ_BENCH_XSHIFT"):  # development: the same mesh moved along x (the coordinate magnitudes of the 8-GPU slabs on fewer GPUs); shown in config.workload
+    XMIN, XMAX = [XMIN[0] + float(os.environ["CQ_BENCH_XSHIFT"]), XMIN[1]], [XMAX[0] + float(os.environ["CQ_BENCH_XSHIFT"]), XMAX[1]]
 BOX3 = [[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]]  # demo/poisson.py:48-49
 FORMS = [("q1_stiffness", 1, "stiffness"), ("q1_mass", 1, "mass"), ("q2_stiffness", 2, "stiffness"), ("q2_mass", 2, "mass")]
 RTOL = 1e-12  # north_star: values within 1e-12 relative
@@ -230,7 +232,7 @@ def run_reference(args):
 
 def workload_config(n_gpus, kernel_path="moment", fused_zero=False):
     return {
-        "workload": f"2-D Q1+Q2 stiffness+mass, {MESH_N * n_gpus}x{MESH_N} quad mesh ({MESH_N}x{MESH_N} per GPU), synthetic ragged runtime quadrature U{{{NQ_LO}..{NQ_HI}}} pts/cell, all cells listed (BASELINE.json configs[1])",
+        "workload": f"2-D Q1+Q2 stiffness+mass, {MESH_N * n_gpus}x{MESH_N} quad mesh ({MESH_N}x{MESH_N} per GPU), synthetic ragged runtime quadrature U{{{NQ_LO}..{NQ_HI}}} pts/cell, all cells listed (BASELINE.json configs[1])" + (f" [development: mesh shifted along x, CQ_BENCH_XSHIFT={os.environ['CQ_BENCH_XSHIFT']}]" if os.environ.get("CQ_BENCH_XSHIFT") else ""),
         "cells_per_gpu": MESH_N * MESH_N, "forms": [f[0] for f in FORMS], "mean_points_per_cell": (NQ_LO + NQ_HI) / 2,
         "l2": "inputs (>= 4 GB of points per pass) are larger than the 126 MB L2; no explicit flush",
         "parallelism": f"cells{n_gpus}" if n_gpus > 1 else "single",

@@ -245,9 +245,6 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NMW3
 #define CQ_MOMENT_NMW3 4
 #endif
-#ifndef CQ_MOMENT_LONG3  // mean points per cell above which the Q1 hexahedron kernels use two large stage slots
-#define CQ_MOMENT_LONG3 36
-#endif
 #ifndef CQ_MOMENT_NPP3   // producer warps per stage slot, Q1 hexahedra
 #define CQ_MOMENT_NPP3 1
 #endif
@@ -312,10 +309,6 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // 0.491 -> 0.466 ms; with U{8..27} points six slots no longer hold a stage and cost 0.60 -> 0.80 ms)
         if (P.num_points <= 12 * P.num_entries)
           return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
-        // long rules (real cut cells of config 3: ~110 points per cell): 32 entries no longer fit a quarter of the shared
-        // memory and the overflowing entries would be read straight from global memory -> two slots of twice the size
-        if (P.num_points > CQ_MOMENT_LONG3 * P.num_entries)
-          return launch_moment_split<T, CQ_MOMENT_G3, 2, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
         return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
       }
     }
