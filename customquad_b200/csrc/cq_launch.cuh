@@ -245,6 +245,18 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NMW3
 #define CQ_MOMENT_NMW3 4
 #endif
+#ifndef CQ_MOMENT_LONG3  // Q1 hexahedra: mean points per cell above which the long-rule shape is used
+#define CQ_MOMENT_LONG3 32
+#endif
+#ifndef CQ_MOMENT_NMW3L  // ... its moment warps (NPW3L producers + NMW3L + 2 expansion warps)
+#define CQ_MOMENT_NMW3L 10
+#endif
+#ifndef CQ_MOMENT_NPW3L  // ... its stage slots
+#define CQ_MOMENT_NPW3L 4
+#endif
+#ifndef CQ_MOMENT_LONG3_3SLOT  // ... up to this mean three slots (a whole stage fits in 73 KB)
+#define CQ_MOMENT_LONG3_3SLOT 56
+#endif
 #ifndef CQ_MOMENT_NPP3   // producer warps per stage slot, Q1 hexahedra
 #define CQ_MOMENT_NPP3 1
 #endif
@@ -309,6 +321,18 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // 0.491 -> 0.466 ms; with U{8..27} points six slots no longer hold a stage and cost 0.60 -> 0.80 ms)
         if (P.num_points <= 12 * P.num_entries)
           return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
+        // long rules (real cut cells carry ~110 points in 3-D, config 3): the kernel is bound by the serial point
+        // loops of its moment lanes, not by bytes (4 moment warps: 0.27 of the HBM roofline at U{40..60} points per cell,
+        // 0.24 at U{100..120}, 0.23 at U{200..300}) -> ten moment warps and one expansion set (16 warps, 128 registers:
+        // 0.36 / 0.33 / 0.29; cut-cell stiffness of config 3 0.66 -> 0.54 ms).  Where three stage slots hold a whole
+        // stage and four do not (mean of 33..56 points per cell) three slots keep every entry in shared memory (U{40..60}:
+        // 0.53; beyond that the entries that overflow are read from global memory by the point loops either way and the
+        // deeper ring wins).  profiles/r2s3/call1_long_rule_shapes_sg8.log
+        if (P.num_points > (int64_t)CQ_MOMENT_LONG3 * P.num_entries) {
+          if (P.num_points <= (int64_t)CQ_MOMENT_LONG3_3SLOT * P.num_entries)
+            return launch_moment_split<T, CQ_MOMENT_G3, 3, CQ_MOMENT_NMW3L, 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
+          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3L, CQ_MOMENT_NMW3L, 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
+        }
         return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
       }
     }

@@ -184,6 +184,10 @@ CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const b
 template <int G, int MPAD>
 CQ_HD constexpr int mom_slot(int k) { return (k % G) * (MPAD / G) + k / G; }
 
+#ifndef CQ_MOMENT_UNROLL3  // points in flight per lane in the hexahedron point loop
+#define CQ_MOMENT_UNROLL3 2
+#endif
+constexpr int kMomentUnroll3 = CQ_MOMENT_UNROLL3;
 template <class T, int G, int CB, int MPAD>
 CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const bool active, const int r, double (&acc)[MPAD]) {
   constexpr int Pn = 3;
@@ -199,7 +203,7 @@ CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const 
   // profiles/r2/ncu_src_hexq1_stiffness_8pt_before.txt); rotated by e / 2 they tile all 32 banks twice.
   int rot = 0;
   if (nq > 1) rot = (e >> 1) & ((1 << (31 - __clz(nq))) - 1);
-#pragma unroll 2
+#pragma unroll kMomentUnroll3
   for (int q0 = r; q0 < nq; q0 += G) {
     int q = q0 + rot;
     if (q >= nq) q -= nq;

@@ -205,12 +205,13 @@ def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
     assert mesh_on_device(dist, torch.device("cuda", torch.cuda.current_device()))[2] == 0
 
 
-@pytest.mark.parametrize("nq_lo,nq_hi", [(0, 40), (40, 200)], ids=["short", "long-rules"])
+@pytest.mark.parametrize("nq_lo,nq_hi", [(0, 40), (36, 52), (40, 200)], ids=["short", "long-rules-3-slots", "long-rules"])
 @pytest.mark.parametrize("bs", [1, 3])
 def test_moment_kernel_hexahedra(cuda_backend, oracle_backend, bs, nq_lo, nq_hi):
     """Axis-aligned Q1 hexahedra (create_box) take the 27-moment kernel for mass / stiffness; with rules of 40..200
     points per cell (real cut cells: config 3) most entries of a stage overflow its shared-memory slice and are read
-    from global memory."""
+    from global memory; means of 33..56 points per cell take the three-slot shape of the long-rule kernel
+    (cq_launch.cuh:launch_auto)."""
     from customquad_b200.assemble import mesh_on_device, set_variant
     import torch
 
