@@ -664,7 +664,8 @@ def config3_leg(dev, peak):
     par = {"stiffness_cut": sample_parity(fK, qb.select(pick), A, T), "nitsche_cut": sample_parity(fN, qs.select(pick), A, T)}
     out = {"workload": f"sphere on Q1 hexahedra {N3}^3: 8-point rule on the {U} uncut cells, device-generated cut-cell rules on the {len(cut)} cut cells (volume) + surface rules with normals (Nitsche) (BASELINE.json configs[2])",
            "cells": int(mesh.num_cells), "cut_cells": int(len(cut)), "bulk_points": int(qb.num_points), "surface_points": int(qs.num_points),
-           "producer_ms": producer_ms, "ms_per_step": ms, "per_kernel_ms": ms_k, "element_tensors_per_s": (U + 2 * len(cut)) / (ms * 1e-3), "csr_nnz_per_s": A.nnz / (ms * 1e-3),
+           "producer_ms": producer_ms, "ms_per_step": ms, "per_kernel_ms": ms_k,
+           "zeroing": "A <- 0 as part of the first call of the step (cq_assemble_matrix_zero: a memset before the kernel unless --fused-zero); per_kernel_ms times each kernel alone, adding to A, and a memset of A", "element_tensors_per_s": (U + 2 * len(cut)) / (ms * 1e-3), "csr_nnz_per_s": A.nnz / (ms * 1e-3),
            "roofline": {"bound": "hbm", "algorithmic_bytes": ab, "achieved_gbs": ab / ms / 1e6, "peak": peak, "frac": ab / ms / 1e6 / peak},
            "volume_rel_err": abs(vol - 4 * np.pi / 3) / (4 * np.pi / 3), "area_rel_err": abs(area - 4 * np.pi) / (4 * np.pi),
            "parity": {"checked": True, **{k: v for k, v in par.items()}, "ok": all(v["ok"] for v in par.values()),
@@ -805,8 +806,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
-    if args.fused_zero:
-        asm.set_fused_zero(True)
+    if args.fused_zero or args.no_fused_zero:
+        asm.set_fused_zero(args.fused_zero)
 
     log("building problem")
     mesh, spaces, fl, qr, slab = build_problem(MESH_N, MESH_N, rank, world)
@@ -1083,7 +1084,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (N=1: general cells, list input; N>1: config 5, also CQ_BENCH_C5=0)")
-    ap.add_argument("--fused-zero", action="store_true", help="zero the matrices inside the moment kernels (cq_ctx_set_fused_zero)")
+    ap.add_argument("--fused-zero", action="store_true", help="zero the matrices inside the moment kernels wherever a kernel can (cq_ctx_set_fused_zero(1); default: the library's policy, a memset first)")
+    ap.add_argument("--no-fused-zero", action="store_true", help="development: never zero inside the kernels (memset first)")
     ap.add_argument("--forms", default="", help="development only: comma-separated subset of the workload's forms (changes the workload; shown in config.forms)")
     ap.add_argument("--only-config", type=int, default=0, choices=[0, 3, 4], help="run just the extra leg of BASELINE.json configs[N-1] on one GPU and print its JSON (tests/test_gpu_full_size.py; not the contract line)")
     args = ap.parse_args()
@@ -1093,6 +1095,10 @@ def main():
         torch.cuda.set_device(0)
         dev = torch.device("cuda", 0)
         peak, _ = measured_peak()
+        if args.no_fused_zero or args.fused_zero:
+            from customquad_b200 import assemble as asm
+
+            asm.set_fused_zero(args.fused_zero)
         out = (config3_leg if args.only_config == 3 else config4_leg)(dev, peak)
         emit({"only_config": args.only_config, **out})
         sys.exit(0 if out.get("skipped") or out["parity"]["ok"] else 3)

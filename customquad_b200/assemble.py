@@ -207,10 +207,11 @@ class _Call:
         return None if self.space is None else C.byref(self.space)
 
 
-def set_fused_zero(on: bool) -> None:
-    """Switches the in-kernel zeroEntries of ``assemble_matrix(..., zero=True)`` on or off for this device
-    (cq_ctx_set_fused_zero; off by default, see include/cq_b200.h)."""
-    _lib.check(_lib.load().cq_ctx_set_fused_zero(_lib.ctx(_dev().index), int(bool(on))))
+def set_fused_zero(on) -> None:
+    """The in-kernel zeroEntries of ``assemble_matrix(..., zero=True)`` on this device (cq_ctx_set_fused_zero):
+    True = wherever a kernel can (mass / stiffness on quadrilaterals and Q1 hexahedra), False = never (memset first),
+    None = the library's default (where it was measured to pay: nowhere so far, see include/cq_b200.h)."""
+    _lib.check(_lib.load().cq_ctx_set_fused_zero(_lib.ctx(_dev().index), -1 if on is None else int(bool(on))))
 
 
 def create_matrix(form: Form, pattern_cells=None, zero: bool = True, facets=None) -> CSRMatrix:

@@ -365,7 +365,7 @@ int cq_ctx_create(int device, cq_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->coop_launch = prop.cooperativeLaunch;
-  c->fused_zero = 0;
+  c->fused_zero = 2;
   int rc = check_cuda(cudaMalloc(&c->err_flag, 2 * sizeof(int)), "cudaMalloc(err_flag)");
   if (!rc) rc = check_cuda(cudaMemset(c->err_flag, 0, 2 * sizeof(int)), "cudaMemset(err_flag)");
   if (!rc) rc = check_cuda(cudaMalloc(&c->work_counter, sizeof(unsigned int)), "cudaMalloc(work_counter)");
@@ -458,7 +458,7 @@ static int assemble_matrix_impl(cq_ctx* ctx, const cq_form_desc* form, const cq_
 
 int cq_ctx_set_fused_zero(cq_ctx* ctx, int on) {
   if (!ctx) { set_error("null ctx"); return CQ_ERR_INVALID; }
-  ctx->fused_zero = on != 0;
+  ctx->fused_zero = on < 0 ? 2 : (on != 0);
   return CQ_OK;
 }
 

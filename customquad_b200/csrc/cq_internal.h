@@ -31,7 +31,7 @@ struct cq_ctx {
   double* scalar_dev = nullptr;  // device accumulator of the host-buffer scalar path
   // fused zeroing (cq_zero.cuh): per-wave value ranges + completion counters, grow-only
   int coop_launch = 0;  // device supports cooperative launches
-  int fused_zero = 0;   // cq_ctx_set_fused_zero
+  int fused_zero = 2;   // cq_ctx_set_fused_zero: 0 off, 1 on, 2 where measured to pay (cq_launch.cuh:fused_zero_ok)
   void* zero_buf = nullptr;
   size_t zero_waves = 0;
   // cut-cell producers: compacted list of the cells the box test calls cut (+ its length), grow-only

@@ -32,6 +32,9 @@ static int ensure_smem_optin(cq_ctx* ctx, const void* kernel, size_t smem) {
   return CQ_OK;
 }
 
+#ifndef CQ_DYNAMIC_ROUNDS
+#define CQ_DYNAMIC_ROUNDS 512
+#endif
 // ---- fused zeroEntries (cq_zero.cuh) ----------------------------------------------------------------
 // Sets P.zero_hi / zero_done / zero_ahead for a launch of `grid` CTAs (stream-ordered).  The caller has checked that
 // the kernel supports it; on return P.zero_req is cleared.
@@ -65,9 +68,6 @@ static int prepare_fused_zero(cq_ctx* ctx, KParams& P, const int n, const int gr
 
 // Stage distribution of a persistent launch: dynamic tickets for long lists (more than CQ_DYNAMIC_ROUNDS rounds of
 // grid * slots stages; see staged_producer), the static interleaving otherwise (one dependent round trip less per stage).
-#ifndef CQ_DYNAMIC_ROUNDS
-#define CQ_DYNAMIC_ROUNDS 512
-#endif
 // heavy: stages that take so long (Q2 hexahedra: a 27 x 27 tensor-core contraction and 729 bs scattered values per
 // entry) that the ticket's round trip is noise -- always dynamic (measured on config 4, 128^3: 68.7 -> 61.7 ms).
 static int choose_dynamic(cq_ctx* ctx, KParams& P, const int64_t num_stages, const int64_t per_round, cudaStream_t s, const bool heavy = false) {
@@ -138,8 +138,23 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
 
 // Can the persistent moment kernels zero the matrix themselves (cq_zero.cuh)?  Not with peer rows: the neighbour's
 // kernel adds into this matrix at any time.
-static bool fused_zero_ok(const cq_ctx* ctx, const KParams& P) {
-  return P.zero_req && ctx->fused_zero && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
+// ctx->fused_zero: 0 never, 1 wherever a kernel carries the zeroing warp, 2 (default) where it was measured to pay --
+// nowhere so far.  Quadrilaterals: the zeroing warp takes the place of a moment warp, 5.2 -> 5.6 ms on the bench
+// workload.  Q1 hexahedra (a 15th warp, no register cost): correct (tests/test_gpu_fused_zero.py) but the kernel with
+// the zeroing warp is slower than memset + kernel -- 128^3 cells, 8 points: 0.707 vs 0.587 ms; config 3 at 256^3: 2.42
+// vs 2.38 ms per step (profiles/r2s3/call2_hex_fused_zero_unroll4_nitsche_warps.log).
+#ifndef CQ_FUSED_ZERO_AUTO_HEX
+#define CQ_FUSED_ZERO_AUTO_HEX 0
+#endif
+static bool fused_zero_ok(const cq_ctx* ctx, const KParams& P, const bool hex = false) {
+  const bool on = ctx->fused_zero == 1 || (ctx->fused_zero == 2 && hex && CQ_FUSED_ZERO_AUTO_HEX);
+  return P.zero_req && on && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
+}
+// ... and only where the stages are dealt out statically (the zeroing front follows the waves of the static
+// interleaving; lists long enough for tickets / traversal tiles keep the memset)
+static bool fused_zero_ok_static(const cq_ctx* ctx, const KParams& P, const int slots) {
+  const int64_t num_stages = (P.num_entries + 31) / 32;
+  return fused_zero_ok(ctx, P, true) && num_stages <= (int64_t)CQ_DYNAMIC_ROUNDS * ctx->num_sms * slots && P.tile_sp == 0;
 }
 
 template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1, int ZW = 0>
@@ -172,7 +187,7 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
   if (P.zero_req) {
     // fused zeroEntries (cq_zero.cuh); not with peer rows (the neighbour's kernel adds into this matrix at any time)
-    if (ZW && fused_zero_ok(ctx, P)) {
+    if (ZW && fused_zero_ok(ctx, P, T::DIM == 3)) {
       if (int rc = prepare_fused_zero(ctx, P, T::N, grid, s)) return rc;
       void* args[] = {(void*)&P};
       ctx->launches++;
@@ -319,8 +334,12 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // short rules (the 8-point bulk rule of config 5): the stages are small and the ring is bound by the stage
         // rate, not by bytes -> six slots (measured on 128^3 cells, 8 points: stiffness 0.513 -> 0.475 ms, mass
         // 0.491 -> 0.466 ms; with U{8..27} points six slots no longer hold a stage and cost 0.60 -> 0.80 ms)
-        if (P.num_points <= 12 * P.num_entries)
+        // (fused zeroEntries: one more warp, 15 or 13 in all, still 128 registers)
+        if (P.num_points <= 12 * P.num_entries) {
+          if (fused_zero_ok_static(ctx, P, CQ_MOMENT_NPW3_SHORT))
+            return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3, 1>(ctx, P, s);
           return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
+        }
         // long rules (real cut cells carry ~110 points in 3-D, config 3): the kernel is bound by the serial point
         // loops of its moment lanes, not by bytes (4 moment warps: 0.27 of the HBM roofline at U{40..60} points per cell,
         // 0.24 at U{100..120}, 0.23 at U{200..300}) -> ten moment warps and one expansion set (16 warps, 128 registers:
@@ -333,6 +352,8 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
             return launch_moment_split<T, CQ_MOMENT_G3, 3, CQ_MOMENT_NMW3L, 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
           return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3L, CQ_MOMENT_NMW3L, 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
         }
+        if (fused_zero_ok_static(ctx, P, CQ_MOMENT_NPW3))
+          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3, 1>(ctx, P, s);
         return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
       }
     }

@@ -184,11 +184,17 @@ CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const b
 template <int G, int MPAD>
 CQ_HD constexpr int mom_slot(int k) { return (k % G) * (MPAD / G) + k / G; }
 
-#ifndef CQ_MOMENT_UNROLL3  // points in flight per lane in the hexahedron point loop
+// UNR: points in flight per lane.  Two for the short / medium shapes; the long-rule shape (ten moment warps,
+// cq_launch.cuh) takes four: most of its entries overflow the stage and are read from global memory, where the loop is
+// bound by the loads in flight (measured with ten moment warps, 96^3 cells: U{100..120} points per cell 1.59 -> 1.26 ms,
+// U{200..300} 3.97 -> 3.36 ms; U{8..27} on the medium shape 0.300 -> 0.309 ms, so not there)
+#ifndef CQ_MOMENT_UNROLL3
 #define CQ_MOMENT_UNROLL3 2
 #endif
-constexpr int kMomentUnroll3 = CQ_MOMENT_UNROLL3;
-template <class T, int G, int CB, int MPAD>
+#ifndef CQ_MOMENT_UNROLL3L
+#define CQ_MOMENT_UNROLL3L 4
+#endif
+template <class T, int G, int CB, int MPAD, int UNR = CQ_MOMENT_UNROLL3>
 CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const bool active, const int r, double (&acc)[MPAD]) {
   constexpr int Pn = 3;
   auto S = [](int k) constexpr { return mom_slot<G, MPAD>(k); };
@@ -203,7 +209,7 @@ CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const 
   // profiles/r2/ncu_src_hexq1_stiffness_8pt_before.txt); rotated by e / 2 they tile all 32 banks twice.
   int rot = 0;
   if (nq > 1) rot = (e >> 1) & ((1 << (31 - __clz(nq))) - 1);
-#pragma unroll kMomentUnroll3
+#pragma unroll UNR
   for (int q0 = r; q0 < nq; q0 += G) {
     int q = q0 + rot;
     if (q >= nq) q -= nq;
@@ -292,7 +298,7 @@ CQ_DEVINL void moment_accumulate_sets(StageMeta<T, CB>& M, const int e, const bo
   }
 }
 
-template <class T, int G, int CB>
+template <class T, int G, int CB, bool LONG = false>
 CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const bool active, const bool compute, const int r) {
   if constexpr (StageMeta<T, CB>::NIT) {
     static_assert(!StageMeta<T, CB>::NIT || G == 4, "Nitsche moment sets: four lanes per entry");
@@ -303,7 +309,7 @@ CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const b
   constexpr int MPAD = round_up(NM, G), B = MPAD / G;
   double acc[MPAD];
   if constexpr (T::DIM == 3) {
-    moment_accumulate3<T, G, CB, MPAD>(M, e, active && compute, r, acc);
+    moment_accumulate3<T, G, CB, MPAD, (LONG ? CQ_MOMENT_UNROLL3L : CQ_MOMENT_UNROLL3)>(M, e, active && compute, r, acc);
   } else {
     double mu[Pn][Pn];
     moment_accumulate<T, G, CB, false>(M, e, active && compute, r, mu);

@@ -21,6 +21,8 @@ tdim = 2 if shape == "quad" else 3
 mesh = cq.create_rectangle([[-1.11, -1.51], [1.55, 1.22]], [N, N]) if tdim == 2 else cq.create_box([[-1.11, -1.51, -1.23], [1.55, 1.22, 1.11]], [N, N, N])
 BS = int(os.environ.get("CQ_BS", "1"))  # block size of the space
 ZERO = os.environ.get("CQ_ZERO", "0") == "1"  # matrices: A.zeroEntries() as part of the call
+if "CQ_FUSED" in os.environ:  # in-kernel zeroing: 1 on, 0 off (default: the library's policy)
+    asm.set_fused_zero(os.environ["CQ_FUSED"] == "1")
 V = cq.FunctionSpace(mesh, ("Lagrange", degree), BS) if BS > 1 else cq.FunctionSpace(mesh, ("Lagrange", degree))
 qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), tdim, lo, hi, seed=5, normals=True)
 dev = torch.device("cuda", 0)

@@ -23,7 +23,7 @@ def fused_zero_on():
         pytest.skip("no CUDA device")
     asm.set_fused_zero(True)
     yield
-    asm.set_fused_zero(False)
+    asm.set_fused_zero(None)
 
 
 def _mesh(tdim, n):
@@ -92,7 +92,8 @@ def test_fused_zero_matches_zero_then_assemble(tdim, degree, bs, kind, n, order)
 
 def test_fused_zero_other_kernels_fall_back_to_memset():
     """Distorted mesh (point-by-point staged kernel) and Q2 hexahedra (tensor-core kernel): same contract.
-    (So do the hexahedron cases above: only the quadrilateral moment kernels carry the zeroing warp.)"""
+    (So does the hexahedron Nitsche case above: the quadrilateral and the Q1 hexahedron mass / stiffness moment
+    kernels carry the zeroing warp.)"""
     rng = np.random.default_rng(9)
     mesh = _mesh(2, 40)
     mesh.geometry.x[:, :2] += rng.uniform(-0.2, 0.2, size=(mesh.geometry.x.shape[0], 2)) * mesh.h()
@@ -103,12 +104,18 @@ def test_fused_zero_other_kernels_fall_back_to_memset():
     _check(forms.mass(V), synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 3, 3, 11, seed=3))
 
 
-def test_zero_in_call_without_fused_zeroing():
-    """Default ctx (fused zeroing off): cq_assemble_matrix_zero = memset + kernel."""
-    asm.set_fused_zero(False)
+@pytest.mark.parametrize("mode", [False, None], ids=["off", "default"])
+def test_zero_in_call_without_fused_zeroing(mode):
+    """Fused zeroing off / the library's default policy: cq_assemble_matrix_zero = memset + kernel."""
+    asm.set_fused_zero(mode)
     mesh = _mesh(2, 60)
     V = _space(mesh, 2, 1)
     _check(forms.mass(V), synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 2, 3, 11, seed=3))
+    mesh = _mesh(3, 34)
+    V = _space(mesh, 1, 1)
+    _check(forms.stiffness(V), synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 3, 8, 8, seed=3))  # short-rule shape
+    _check(forms.stiffness(V), synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 3, 8, 27, seed=3))
+    _check(forms.stiffness(V), synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), 3, 40, 120, seed=3))  # long rules: memset
 
 
 def test_fused_zero_empty_list_zeroes():
