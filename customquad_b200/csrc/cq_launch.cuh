@@ -248,6 +248,15 @@ struct StagedShape {
 #ifndef CQ_MOMENT_SG
 #define CQ_MOMENT_SG 4
 #endif
+#ifndef CQ_MOMENT_LONG2  // quadrilaterals: mean points per cell above which the long-rule shape is used (measured: the
+#define CQ_MOMENT_LONG2 48  // bench workload, mean 40, loses 4 % in it; U{40..80}, mean 60, gains 23 % (Q2) / 4 % (Q1))
+#endif
+#ifndef CQ_MOMENT_NMW2Z  // Q2 quadrilaterals with the zeroing warp: moment warps / expansion sets (4 + NMW2Z + 3 NXS2Z + 1 <= 16)
+#define CQ_MOMENT_NMW2Z (CQ_MOMENT_NMW2 - 1)
+#endif
+#ifndef CQ_MOMENT_NXS2Z
+#define CQ_MOMENT_NXS2Z CQ_MOMENT_NXS2
+#endif
 #ifndef CQ_MOMENT_G3    // Q1 hexahedra: lanes per entry in the point loop, moment warps, expansion warp sets
 #define CQ_MOMENT_G3 2
 #endif
@@ -281,8 +290,8 @@ struct StagedShape {
 #ifndef CQ_NITSCHE_NMW3  // Nitsche moment kernel (Q1 hexahedra): moment warps / expansion sets (3 stage slots)
 #define CQ_NITSCHE_NMW3 6
 #endif
-#ifndef CQ_NITSCHE_NXS3
-#define CQ_NITSCHE_NXS3 1
+#ifndef CQ_NITSCHE_NXS3  // three sets = one per stage slot (15 warps, 128 registers): U{4..16} surface points per cell 0.61 -> 0.49 ms
+#define CQ_NITSCHE_NXS3 3
 #endif
 #ifndef CQ_MOMENT_NPP  // producer warps per stage slot
 #define CQ_MOMENT_NPP 1
@@ -313,7 +322,14 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
           // of a moment warp (a 17th warp costs the registers of 20: 96 per thread, spills in the point loop)
           constexpr int NMW = T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2;
           constexpr int NXW = (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1);
-          if (fused_zero_ok(ctx, P)) return launch_moment_split<T, CQ_MOMENT_SG, 4, NMW - (T::DEG == 2 ? 1 : 0), NXW, true, CQ_MOMENT_NPP, 1>(ctx, P, s);
+          if (fused_zero_ok(ctx, P))
+            return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 2 ? CQ_MOMENT_NMW2Z : NMW), (T::DEG == 2 ? CQ_MOMENT_NXS2Z * 3 : NXW), true, CQ_MOMENT_NPP, 1>(ctx, P, s);
+          // long rules: as on hexahedra, the serial point loops bind -> more moment warps (Q1 4 + 10 + 2, Q2 4 + 9 + 3:
+          // one expansion set) and four points in flight per lane.  1024^2 cells: Q2 stiffness U{200..300} points per
+          // cell 3.70 -> 2.11 ms (0.29 -> 0.51 of the HBM roofline), Q2 mass U{80..120} 1.57 -> 0.91, Q1 stiffness
+          // U{80..120} 1.03 -> 0.66 (0.40 -> 0.63); profiles/r2s3/call3_quad_long_shape_unroll_nitsche_sets.log
+          if (P.num_points > (int64_t)CQ_MOMENT_LONG2 * P.num_entries)
+            return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 1 ? 10 : 9), T::DEG + 1, true, CQ_MOMENT_NPP, 0>(ctx, P, s);
           return launch_moment_split<T, CQ_MOMENT_SG, 4, NMW, NXW, true, CQ_MOMENT_NPP, 0>(ctx, P, s);
         }
         if (split) return launch_moment_split<T, CQ_MOMENT_SG, 4, CQ_MOMENT_NMW, T::DEG == 1 ? 2 : CQ_MOMENT_NXW1, false, 1, 0>(ctx, P, s);

@@ -130,10 +130,19 @@ CQ_HD constexpr int pair_owner(int idx) {
   return NXW == 3 ? o3[idx] : (NXW == 2 ? o2[idx] : idx % NXW);
 }
 
+// points in flight per lane in the quadrilateral point loop: two on the bench workload (U{16..64} points per cell:
+// three cost 5.23 -> 5.32 ms per step, four 5.42), four in the long-rule shape (cq_launch.cuh; Q2 stiffness at
+// U{200..300} points per cell 2.71 -> 2.11 ms, Q1 at U{80..120} 0.87 -> 0.66 ms)
+#ifndef CQ_MOMENT_UNROLL2
+#define CQ_MOMENT_UNROLL2 2
+#endif
+#ifndef CQ_MOMENT_UNROLL2L
+#define CQ_MOMENT_UNROLL2L 4
+#endif
 // T: FormTraits with DIM == 2 and FORM in {MASS, STIFFNESS}.
 // Point loop: G lanes per entry, lane r takes the points r, r+G, ...; the moments are all-reduced over
 // the group (every lane ends with the full set).
-template <class T, int G, int CB, bool ALLREDUCE = true>
+template <class T, int G, int CB, bool ALLREDUCE = true, int UNR = CQ_MOMENT_UNROLL2>
 CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const bool active, const int r,
                                  double (&mu)[2 * T::DEG + 1][2 * T::DEG + 1]) {
   constexpr int Pn = 2 * T::DEG + 1;
@@ -144,7 +153,7 @@ CQ_DEVINL void moment_accumulate(const StageMeta<T, CB>& M, const int e, const b
   const int nq = active ? M.nq[e] : 0;
   const double* pp = M.pts[e];
   const double* wp = M.w[e];
-#pragma unroll 2
+#pragma unroll UNR
   for (int q = r; q < nq; q += G) {
     const double2 xy = *reinterpret_cast<const double2*>(pp + 2 * q);
     const double w = wp[q];
@@ -312,7 +321,7 @@ CQ_DEVINL void moment_accumulate_store(StageMeta<T, CB>& M, const int e, const b
     moment_accumulate3<T, G, CB, MPAD, (LONG ? CQ_MOMENT_UNROLL3L : CQ_MOMENT_UNROLL3)>(M, e, active && compute, r, acc);
   } else {
     double mu[Pn][Pn];
-    moment_accumulate<T, G, CB, false>(M, e, active && compute, r, mu);
+    moment_accumulate<T, G, CB, false, (LONG ? CQ_MOMENT_UNROLL2L : CQ_MOMENT_UNROLL2)>(M, e, active && compute, r, mu);
 #pragma unroll
     for (int k = 0; k < MPAD; ++k) acc[k] = 0.0;
 #pragma unroll

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
             if (e0 >= nent) break;
             const bool active = e0 + grp < nent;
             const int e = active ? M.order[e0 + grp] : 0;
-            moment_accumulate_store<T, G, CB, (T::DIM == 3 && NMW >= 8)>(M, e, active, CQ_DBG(P) != 1, r);
+            moment_accumulate_store<T, G, CB, (NMW >= 9)>(M, e, active, CQ_DBG(P) != 1, r);  // long-rule shapes: more points in flight
           }
         }
         __syncwarp();

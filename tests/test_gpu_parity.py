@@ -179,10 +179,13 @@ def test_input_conventions(cuda_backend, oracle_backend):
     assert close(A.data, oracle_backend.matrix(forms.mass(V), [(cells, P2, W2)]).data)
 
 
+@pytest.mark.parametrize("nq_lo,nq_hi", [(0, 70), (40, 200)], ids=["short", "long-rules"])
 @pytest.mark.parametrize("degree,bs", [(1, 1), (2, 1), (1, 2), (2, 2)])
-def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
+def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs, nq_lo, nq_hi):
     """Axis-aligned quadrilateral meshes take the monomial-moment kernel for mass / stiffness
-    (cq_moment.cuh); the result must equal both the oracle and the point-by-point kernels."""
+    (cq_moment.cuh); the result must equal both the oracle and the point-by-point kernels.  A mean of more than 64
+    points per cell takes the long-rule shape (more moment warps, four points in flight per lane; entries that
+    overflow a stage are read from global memory)."""
     from customquad_b200.assemble import mesh_on_device, set_variant
     import torch
 
@@ -191,7 +194,7 @@ def test_moment_kernel_matches_oracle(cuda_backend, oracle_backend, degree, bs):
     V = cq.FunctionSpace(mesh, ("Lagrange", degree)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", degree))
     rng = np.random.default_rng(31)
     cells = np.concatenate([rng.permutation(mesh.num_cells), rng.integers(0, mesh.num_cells, 40)])
-    qr = synthetic_ragged(cells, 2, 0, 70, seed=13, normals=True)
+    qr = synthetic_ragged(cells, 2, nq_lo, nq_hi, seed=13, normals=True)
     for form in (forms.mass(V), forms.stiffness(V)):
         R = oracle_backend.matrix(form, [qr])
         set_variant(0)
