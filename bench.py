@@ -230,14 +230,15 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(n_gpus, kernel_path="moment", fused_zero=False):
+def workload_config(n_gpus, kernel_path="moment", fused_zero=None):
     return {
         "workload": f"2-D Q1+Q2 stiffness+mass, {MESH_N * n_gpus}x{MESH_N} quad mesh ({MESH_N}x{MESH_N} per GPU), synthetic ragged runtime quadrature U{{{NQ_LO}..{NQ_HI}}} pts/cell, all cells listed (BASELINE.json configs[1])" + (f" [development: mesh shifted along x, CQ_BENCH_XSHIFT={os.environ['CQ_BENCH_XSHIFT']}]" if os.environ.get("CQ_BENCH_XSHIFT") else ""),
         "cells_per_gpu": MESH_N * MESH_N, "forms": [f[0] for f in FORMS], "mean_points_per_cell": (NQ_LO + NQ_HI) / 2,
         "l2": "inputs (>= 4 GB of points per pass) are larger than the 126 MB L2; no explicit flush",
         "parallelism": f"cells{n_gpus}" if n_gpus > 1 else "single",
         "kernel_path": kernel_path + (" (monomial-moment kernels: every cell of the tensor mesh is axis-aligned; the general-cell point-by-point path is timed in extra.general_cells)" if kernel_path == "moment" else " (point-by-point kernels)"),
-        "zeroing": "in-kernel (cq_ctx_set_fused_zero)" if fused_zero else "memset before the kernel",
+        "zeroing": {True: "in-kernel wherever a kernel can (cq_ctx_set_fused_zero(1))", False: "memset before every kernel (cq_ctx_set_fused_zero(0))",
+                    None: "library default (cq_ctx_set_fused_zero(-1)): a memset before the kernel, except the Q2 mass matrix, zeroed inside its kernel"}[fused_zero],
         "parity_pinned_by_reference_tests": "Q1 mass-type only (test/test_linear_basis.py); Q1/Q2 stiffness and Q2 mass are pinned by sympy closed forms and the demo's convergence (DESIGN.md 6)",
         "exchange": "interface rows of the neighbour rank: red.global.add.f64 into peer memory over NVLink from the assembly kernels, neighbour fences through peer-memory flags (CQ_PEER_SCATTER=0: ncclSend/ncclRecv + accumulate kernel, cq_exchange_offrank)" if n_gpus > 1 else "none",
     }  # fmt: skip
@@ -1038,7 +1039,7 @@ def run_gpu(args):
     line = {
         "metric": "element_tensors_per_s", "value": len(fl) * C_cells * world / (ms_step * 1e-3), "unit": "element tensors/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, kernel_path, args.fused_zero),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, kernel_path, True if args.fused_zero else (False if args.no_fused_zero else None)),
         "csr_nnz_per_s": sum(k["nnz"] for k in kern) * world / (ms_step * 1e-3),
         "per_form_ms": dict(zip([f[0] for f in fl], per_form_ms)),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

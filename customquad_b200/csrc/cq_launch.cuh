@@ -138,23 +138,23 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
 
 // Can the persistent moment kernels zero the matrix themselves (cq_zero.cuh)?  Not with peer rows: the neighbour's
 // kernel adds into this matrix at any time.
-// ctx->fused_zero: 0 never, 1 wherever a kernel carries the zeroing warp, 2 (default) where it was measured to pay --
-// nowhere so far.  Quadrilaterals: the zeroing warp takes the place of a moment warp, 5.2 -> 5.6 ms on the bench
-// workload.  Q1 hexahedra (a 15th warp, no register cost): correct (tests/test_gpu_fused_zero.py) but the kernel with
-// the zeroing warp is slower than memset + kernel -- 128^3 cells, 8 points: 0.707 vs 0.587 ms; config 3 at 256^3: 2.42
-// vs 2.38 ms per step (profiles/r2s3/call2_hex_fused_zero_unroll4_nitsche_warps.log).
-#ifndef CQ_FUSED_ZERO_AUTO_HEX
-#define CQ_FUSED_ZERO_AUTO_HEX 0
-#endif
-static bool fused_zero_ok(const cq_ctx* ctx, const KParams& P, const bool hex = false) {
-  const bool on = ctx->fused_zero == 1 || (ctx->fused_zero == 2 && hex && CQ_FUSED_ZERO_AUTO_HEX);
-  return P.zero_req && on && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
+// ctx->fused_zero: 0 never, 1 wherever a kernel carries the zeroing warp, 2 (default) where it was measured to pay:
+// the Q2 quadrilateral MASS kernel in the shape 4 + 8 + 3 + 1 (one expansion set; zero + mass on the bench workload
+// 1.78 -> 1.59 ms, DRAM traffic 9.2 -> 7.0 GB).  Not: Q2 stiffness (its heavier expansion needs the two sets: 1.84 ->
+// 1.90 ms in that shape, 1.98 ms as 4 + 5 + 6 + 1), Q1 quadrilaterals (0.86 -> 0.89 ms), Q1 hexahedra (a 15th warp, no
+// register cost, correct -- tests/test_gpu_fused_zero.py -- but 128^3 cells, 8 points: 0.707 vs 0.587 ms; config 3 at
+// 256^3: 2.42 vs 2.38 ms per step).  profiles/r2s3/call2_*.log, call5_*.log
+static bool fused_zero_possible(const cq_ctx* ctx, const KParams& P) {
+  return P.zero_req && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
+}
+static bool fused_zero_ok(const cq_ctx* ctx, const KParams& P, const bool pays = false) {
+  return (ctx->fused_zero == 1 || (ctx->fused_zero == 2 && pays)) && fused_zero_possible(ctx, P);
 }
 // ... and only where the stages are dealt out statically (the zeroing front follows the waves of the static
 // interleaving; lists long enough for tickets / traversal tiles keep the memset)
 static bool fused_zero_ok_static(const cq_ctx* ctx, const KParams& P, const int slots) {
   const int64_t num_stages = (P.num_entries + 31) / 32;
-  return fused_zero_ok(ctx, P, true) && num_stages <= (int64_t)CQ_DYNAMIC_ROUNDS * ctx->num_sms * slots && P.tile_sp == 0;
+  return fused_zero_ok(ctx, P, false) && num_stages <= (int64_t)CQ_DYNAMIC_ROUNDS * ctx->num_sms * slots && P.tile_sp == 0;
 }
 
 template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1, int ZW = 0>
@@ -187,7 +187,7 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
   if (P.zero_req) {
     // fused zeroEntries (cq_zero.cuh); not with peer rows (the neighbour's kernel adds into this matrix at any time)
-    if (ZW && fused_zero_ok(ctx, P, T::DIM == 3)) {
+    if (ZW && fused_zero_possible(ctx, P)) {  // the caller chose this instantiation by the policy (fused_zero_ok)
       if (int rc = prepare_fused_zero(ctx, P, T::N, grid, s)) return rc;
       void* args[] = {(void*)&P};
       ctx->launches++;
@@ -251,11 +251,11 @@ struct StagedShape {
 #ifndef CQ_MOMENT_LONG2  // quadrilaterals: mean points per cell above which the long-rule shape is used (measured: the
 #define CQ_MOMENT_LONG2 48  // bench workload, mean 40, loses 4 % in it; U{40..80}, mean 60, gains 23 % (Q2) / 4 % (Q1))
 #endif
-#ifndef CQ_MOMENT_NMW2Z  // Q2 quadrilaterals with the zeroing warp: moment warps / expansion sets (4 + NMW2Z + 3 NXS2Z + 1 <= 16)
-#define CQ_MOMENT_NMW2Z (CQ_MOMENT_NMW2 - 1)
+#ifndef CQ_MOMENT_NMW2Z  // Q2 quadrilaterals with the zeroing warp: moment warps / expansion sets (4 + NMW2Z + 3 NXS2Z + 1 <= 16;
+#define CQ_MOMENT_NMW2Z 8  // 4 + 5 + 6 + 1: zero + mass 1.96, zero + stiffness 1.98 ms; 4 + 8 + 3 + 1: 1.59 / 1.90 ms)
 #endif
 #ifndef CQ_MOMENT_NXS2Z
-#define CQ_MOMENT_NXS2Z CQ_MOMENT_NXS2
+#define CQ_MOMENT_NXS2Z 1
 #endif
 #ifndef CQ_MOMENT_G3    // Q1 hexahedra: lanes per entry in the point loop, moment warps, expansion warp sets
 #define CQ_MOMENT_G3 2
@@ -317,12 +317,13 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // split = 2: row-owned expansion + transposed scatter (RowTile, cq_moment.cuh)
         const int split = CQ_TUNE_INT("CQ_MOMENT_SPLIT", 2);
         if (split == 2) {
-          // fused zeroEntries (opt-in, cq_ctx_set_fused_zero): one more warp.  Q1: 4 + 8 + 2 + 1 warps still cost 16
-          // warps' worth of registers; Q2: 4 + 6 + 6 = 16 warps at 128 registers, so the zeroing warp takes the place
-          // of a moment warp (a 17th warp costs the registers of 20: 96 per thread, spills in the point loop)
+          // fused zeroEntries (cq_ctx_set_fused_zero; policy: fused_zero_ok): one more warp.  Q1: 4 + 8 + 2 + 1 warps
+          // still cost 16 warps' worth of registers; Q2: 4 + 6 + 6 = 16 warps at 128 registers and a 17th warp costs the
+          // registers of 20 (96 per thread, spills in the point loop), so the zeroing warp and two more moment warps
+          // take the place of the second expansion set: 4 + 8 + 3 + 1
           constexpr int NMW = T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2;
           constexpr int NXW = (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1);
-          if (fused_zero_ok(ctx, P))
+          if (fused_zero_ok(ctx, P, T::DEG == 2 && T::FORM_ID == CQ_FORM_MASS))
             return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 2 ? CQ_MOMENT_NMW2Z : NMW), (T::DEG == 2 ? CQ_MOMENT_NXS2Z * 3 : NXW), true, CQ_MOMENT_NPP, 1>(ctx, P, s);
           // long rules: as on hexahedra, the serial point loops bind -> more moment warps (Q1 4 + 10 + 2, Q2 4 + 9 + 3:
           // one expansion set) and four points in flight per lane.  1024^2 cells: Q2 stiffness U{200..300} points per

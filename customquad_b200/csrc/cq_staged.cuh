@@ -23,6 +23,9 @@
 #pragma once
 #include "cq_kernels.cuh"
 
+#ifndef CQ_STAGED_UNROLL_VS  // point loop of the vector / scalar kernels with at most 16 accumulators: points in flight per lane
+#define CQ_STAGED_UNROLL_VS 2
+#endif
 namespace cq {
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------------
@@ -186,7 +189,8 @@ CQ_DEVINL void staged_process_entry(const KParams& P, const StageMeta<T, CB>& M,
     const double* wp = M.w[e];
     const double* np_ = T::NEED_NORMAL ? M.nrm[e] : nullptr;
     double (&accT)[T::NACC] = *reinterpret_cast<double (*)[T::NACC]>(&acc[0]);
-#pragma unroll 2
+    constexpr int UNR = (T::RANK < 2 && T::NACC <= 16) ? CQ_STAGED_UNROLL_VS : 2;  // points in flight per lane
+#pragma unroll UNR
     for (int q = r; q < nq; q += G) {
       double xi[DIM], nrm[DIM];
       if constexpr (DIM == 2) {

@@ -204,8 +204,8 @@ int64_t cq_ctx_launch_count(const cq_ctx* ctx);
 int cq_ctx_set_variant(cq_ctx* ctx, int variant);
 /* cq_assemble_matrix_zero zeroes inside the persistent moment kernels (cooperative launch) instead of a memset
  * before them: 1 wherever a kernel can (mass / stiffness on quadrilaterals and Q1 hexahedra), 0 never, -1 = the
- * default: where it was measured to pay -- nowhere so far (it removes a quarter of the DRAM traffic, but the
- * kernels are bound by their load/store pipe, not by bytes).  Same result either way. */
+ * default: where it was measured to pay (the Q2 quadrilateral mass kernel: zero + assemble 1.78 -> 1.59 ms on the
+ * bench workload; the other kernels are bound by their load/store pipe and lose).  Same result either way. */
 int cq_ctx_set_fused_zero(cq_ctx* ctx, int on);
 
 /* ---- the hot path (device pointers) ---------------------------------------------------- */
@@ -217,10 +217,10 @@ int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
  * kernels the zeroing runs inside the kernel, a few stages ahead of the scatter, so the zeroed lines
  * are still in L2 when the element tensors arrive and each line of the matrix crosses the HBM
  * interface once instead of three times (memset write, read-modify-write) -- when the ctx has the
- * fused zeroing switched on (cq_ctx_set_fused_zero; off by default: on the 2048^2 quadrilateral bench
- * workload it moves 7.0 instead of 9.2 GB per Q2 matrix but the step is no faster,
- * profiles/r1/fused_zero_study.md; same finding on Q1 hexahedra).  Otherwise, for every other kernel, for
- * lists long enough for ticketed stages, and for a matrix with peer rows, a memset runs first.  Same result as memset + cq_assemble_matrix. */
+ * fused zeroing applies (cq_ctx_set_fused_zero; by default on the Q2 quadrilateral mass kernel only: it
+ * moves 7.0 instead of 9.2 GB per Q2 matrix, but the other kernels are no faster for it,
+ * profiles/r1/fused_zero_study.md, profiles/r2s3/).  Otherwise, for every other kernel, for lists long
+ * enough for ticketed stages (hexahedra), and for a matrix with peer rows, a memset runs first.  Same result as memset + cq_assemble_matrix. */
 int cq_assemble_matrix_zero(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,
                             const cq_space* space, const cq_quadrature* qr, const cq_csr* A,
                             void* stream);
