@@ -110,11 +110,11 @@ def coefficient_on_device(f, dev):
     """dolfinx.cpp.fem.pack_coefficients (assemble_matrix.py:16): [num_cells, n*bs]."""
     torch = _torch()
     V = f.function_space
-    d = space_on_device(V, dev).to(torch.int64)
+    d = space_on_device(V, dev)  # int32 indices gather directly (no int64 copy of the dofmap per call)
     arr = torch.from_numpy(f.array).to(dev)
     if V.bs == 1:
         return arr[d].contiguous()
-    idx = (d[:, :, None] * V.bs + torch.arange(V.bs, device=dev)[None, None, :]).reshape(d.shape[0], -1)
+    idx = (d.to(torch.int64)[:, :, None] * V.bs + torch.arange(V.bs, device=dev)[None, None, :]).reshape(d.shape[0], -1)
     return arr[idx].contiguous()
 
 

@@ -222,11 +222,14 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
 #ifndef CQ_STAGED_NPW_VS  // stage slots of the vector / scalar kernels with at most 16 accumulators (16 warps in all)
 #define CQ_STAGED_NPW_VS 4
 #endif
+#ifndef CQ_STAGED_NCW_VS3  // consumer warps of the hexahedron kernels with at most 16 accumulators (Q1 vectors, scalars)
+#define CQ_STAGED_NCW_VS3 12
+#endif
 template <class T>
 struct StagedShape {
   static constexpr bool SMALL_VS = T::RANK < 2 && T::NACC <= 16;
   static constexpr int NPW = SMALL_VS ? CQ_STAGED_NPW_VS : 4;
-  static constexpr int NCW = T::NACC <= 16 ? 16 - NPW : (T::NACC <= 36 ? CQ_STAGED_NCW36 : CQ_STAGED_NCW45);
+  static constexpr int NCW = T::NACC <= 16 ? (T::DIM == 3 ? CQ_STAGED_NCW_VS3 : 16 - NPW) : (T::NACC <= 36 ? CQ_STAGED_NCW36 : CQ_STAGED_NCW45);
   static constexpr int G = T::NACC <= 16 ? 4 : (T::NACC <= 36 ? CQ_STAGED_G36 : CQ_STAGED_G45);
 };
 
