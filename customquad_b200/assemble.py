@@ -111,7 +111,9 @@ def coefficient_on_device(f, dev):
     torch = _torch()
     V = f.function_space
     d = space_on_device(V, dev)  # int32 indices gather directly (no int64 copy of the dofmap per call)
-    arr = torch.from_numpy(f.array).to(dev)
+    arr = getattr(f, "device_array", None)  # a Function whose values live on the device (fem.Function.to_device): no upload
+    if arr is None or arr.device != dev:
+        arr = torch.from_numpy(f.array).to(dev)
     if V.bs == 1:
         return arr[d].contiguous()
     idx = (d.to(torch.int64)[:, :, None] * V.bs + torch.arange(V.bs, device=dev)[None, None, :]).reshape(d.shape[0], -1)

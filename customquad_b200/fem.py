@@ -193,11 +193,22 @@ class Function:
         self.function_space = V
         self.array = np.zeros(V.num_dofs) if values is None else np.ascontiguousarray(values, dtype=np.float64)
         assert self.array.shape == (V.num_dofs,)
+        self.device_array = None
         self._dev = {}
 
     @property
     def x(self):
         return SimpleNamespace(array=self.array)
+
+    def to_device(self, dev=None):
+        """Keeps a copy of the values in HBM (``device_array``, a torch tensor): every later assemble_* call with this
+        coefficient packs from it instead of uploading ``array`` (8 MB per call at 1 M dofs).  Call again after changing
+        ``array``; assigning a CUDA tensor to ``device_array`` directly (a solution that never left the GPU) works too."""
+        import torch
+
+        dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
+        self.device_array = torch.from_numpy(self.array).to(dev)
+        return self
 
     def interpolate(self, fcn) -> "Function":
         """Nodal interpolation; ``fcn(x)`` with x of shape [3, npoints] as in dolfinx
@@ -210,6 +221,7 @@ class Function:
         else:
             self.array[:] = np.broadcast_to(vals, (V.bs, V.dofmap.num_dofs)).T.reshape(-1)
         self._dev.clear()
+        self.device_array = None
         return self
 
     def packed(self) -> np.ndarray:

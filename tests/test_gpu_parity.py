@@ -417,3 +417,28 @@ def test_far_from_origin_mesh_matches_recentred_oracle(cuda_backend, oracle_back
             sc = np.abs(R0.data).max()
             assert np.abs(S.data - R.data).max() <= tol * sc
             assert np.abs(S.data - R0.data).max() <= 1e-12 * sc
+
+
+def test_device_resident_coefficient(cuda_backend, oracle_backend):
+    """A coefficient whose values live in HBM (Function.to_device / device_array) packs without an upload and gives the
+    same vectors and functionals as the host array (reference: pack_coefficients, assemble_vector.py:16)."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    for tdim, degree, bs in ((2, 2, 1), (3, 1, 3)):
+        mesh = make_mesh(tdim, True)
+        V = cq.FunctionSpace(mesh, ("Lagrange", degree)) if bs == 1 else cq.VectorFunctionSpace(mesh, ("Lagrange", degree))
+        f = cq.Function(V)
+        f.array[:] = rng.uniform(-1, 1, V.num_dofs)
+        qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), tdim, 1, 9, seed=3, normals=True)
+        lf = forms.load(V, f)
+        ref = oracle_backend.vector(lf, [qr])
+        host = cuda_backend.vector(lf, [qr])
+        f.to_device()
+        assert f.device_array.is_cuda
+        f.array[:] = 0.0  # the device copy is what counts now
+        dev = cuda_backend.vector(lf, [qr])
+        assert np.array_equal(host, dev)
+        assert close(dev, ref)
+        f.device_array = torch.zeros_like(f.device_array)
+        assert np.all(cuda_backend.vector(lf, [qr]) == 0.0)
