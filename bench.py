@@ -238,7 +238,7 @@ def workload_config(n_gpus, kernel_path="moment", fused_zero=None):
         "parallelism": f"cells{n_gpus}" if n_gpus > 1 else "single",
         "kernel_path": kernel_path + (" (monomial-moment kernels: every cell of the tensor mesh is axis-aligned; the general-cell point-by-point path is timed in extra.general_cells)" if kernel_path == "moment" else " (point-by-point kernels)"),
         "zeroing": {True: "in-kernel wherever a kernel can (cq_ctx_set_fused_zero(1))", False: "memset before every kernel (cq_ctx_set_fused_zero(0))",
-                    None: "library default (cq_ctx_set_fused_zero(-1)): a memset before the kernel, except the Q2 mass matrix, zeroed inside its kernel"}[fused_zero],
+                    None: "library default (cq_ctx_set_fused_zero(-1)): a memset before the Q1 kernels; the Q2 matrices are zeroed inside their kernels"}[fused_zero],
         "parity_pinned_by_reference_tests": "Q1 mass-type only (test/test_linear_basis.py); Q1/Q2 stiffness and Q2 mass are pinned by sympy closed forms and the demo's convergence (DESIGN.md 6)",
         "exchange": "interface rows of the neighbour rank: red.global.add.f64 into peer memory over NVLink from the assembly kernels, neighbour fences through peer-memory flags (CQ_PEER_SCATTER=0: ncclSend/ncclRecv + accumulate kernel, cq_exchange_offrank)" if n_gpus > 1 else "none",
     }  # fmt: skip
@@ -898,29 +898,45 @@ def run_gpu(args):
                   "what": "owned interface rows of the 4 matrices on every rank > 0 (result of the last timed step, exchange included) vs the CPU oracle on the two cell layers around the interface; sparsity bit-exact, values (a) on identical inputs to tol = max(1e-12, 4 eps kappa), kappa = max|x| / h of the rank's slab (bench.py:parity_tolerance: the weak-scaling mesh grows with N, and the reference's J = sum_v x_v grad psi_v carries eps kappa of its own), and (b) to 1e-12 against the oracle on the same cells with the geometry translated to put the interface at x = 0 (max_rel_recentred)"}  # fmt: skip
 
     # ---- per-kernel roofline (kernel-only times: separate pass, events around the launch alone) ----
+    # For every form the kernel the timed step runs: where the library zeroes the matrix inside the assembly kernel
+    # (config.zeroing; seen from the launch count of the zeroing call: two small setup kernels + the cooperative kernel)
+    # that is the zeroing kernel, timed through the same call as in the step; otherwise the add-only kernel, timed after a
+    # separate fill.  ms_add_only: the add-only kernel in both cases (the basis of the earlier rounds' numbers).
     peak, peak_src = measured_peak()
     kern = []
     for i, (name, form, deg) in enumerate(fl):
         A = mats[name]
-        ts = []
-        for _ in range(max(3, args.steps)):
-            A.data.zero_()
-            if fused:
-                exch[name].fence(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            asm.assemble_matrix(form, [qr], A=A)
-            e1.record()
-            if fused:
-                exch[name].fence(dev)
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = float(np.mean(ts))
+
+        def timed_add_only():
+            ts = []
+            for _ in range(max(3, args.steps)):
+                A.data.zero_()
+                if fused:
+                    exch[name].fence(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                asm.assemble_matrix(form, [qr], A=A)
+                e1.record()
+                if fused:
+                    exch[name].fence(dev)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return float(np.mean(ts))
+
+        in_kernel = False
+        if world == 1:  # (at N > 1 the form's time in the step includes the exchange: the add-only kernel is reported)
+            l0 = _lib.launch_count(local_rank)
+            asm.assemble_matrix(form, [qr], A=A, zero=True)
+            in_kernel = _lib.launch_count(local_rank) - l0 == 3
+        ms_add = timed_add_only()
+        ms = per_form_ms[i] if in_kernel else ms_add  # in-kernel zeroing: the call inside the timed region is this kernel (+ its two setup kernels)
         n = (deg + 1) ** 2
         ab = algorithmic_bytes(C_cells, P_pts, 2, 4, n, mesh.geometry.x.shape[0], A.nnz)
-        # ms: the kernel alone, adding to a zeroed matrix; ms_in_step: what the form costs inside the timed step, zeroing
-        # included (memset + kernel, or the kernel that zeroes the matrix itself: config.zeroing) and, at N > 1, the fence
+        # ms_in_step: what the form costs inside the timed step, zeroing included (memset + kernel, or the zeroing kernel) and,
+        # at N > 1, the fence
         kern.append({"kernel": name, "ms": ms, "algorithmic_bytes": ab, "achieved_gbs": ab / ms / 1e6, "frac": ab / ms / 1e6 / peak,
+                     "zeroing": "inside this kernel (ms includes it and the two setup kernels of the zeroing ranges)" if in_kernel else "memset before the kernel (a separate launch, not in ms)",
+                     "ms_add_only": ms_add, "frac_add_only": ab / ms_add / 1e6 / peak,
                      "ms_in_step": per_form_ms[i], "frac_in_step": ab / per_form_ms[i] / 1e6 / peak,
                      "nnz": A.nnz, "cells_per_s": C_cells / ms * 1e3})  # fmt: skip
     dom = max(kern, key=lambda k: k["ms"])
@@ -928,8 +944,12 @@ def run_gpu(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(dom["kernel"])
+    ab_step = sum(k["algorithmic_bytes"] for k in kern)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "per_kernel": kern}  # fmt: skip
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "basis": "the kernel the timed step runs for this form; where it zeroes the matrix itself (per_kernel[i].zeroing) its time includes the zeroing, for which the algorithmic bytes give no credit -- per_kernel[i].frac_add_only is the add-only kernel on a zeroed matrix, the basis of round 1's 0.66",
+                "step": {"algorithmic_bytes": ab_step, "ms": ms_step, "frac": ab_step / ms_step / 1e6 / peak, "what": "all four forms, zeroing included"},
+                "per_kernel": kern}  # fmt: skip
 
     # ---- end to end: host (pinned) qr buffers in ONCE per step, CSR values of all four matrices out ----
     e2e = None

@@ -212,7 +212,7 @@ class _Call:
 def set_fused_zero(on) -> None:
     """The in-kernel zeroEntries of ``assemble_matrix(..., zero=True)`` on this device (cq_ctx_set_fused_zero):
     True = wherever a kernel can (mass / stiffness on quadrilaterals and Q1 hexahedra), False = never (memset first),
-    None = the library's default (where it was measured to pay: the Q2 quadrilateral mass kernel, see include/cq_b200.h)."""
+    None = the library's default (where it was measured to pay: the Q2 quadrilateral kernels, see include/cq_b200.h)."""
     _lib.check(_lib.load().cq_ctx_set_fused_zero(_lib.ctx(_dev().index), -1 if on is None else int(bool(on))))
 
 

@@ -139,11 +139,12 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
 // Can the persistent moment kernels zero the matrix themselves (cq_zero.cuh)?  Not with peer rows: the neighbour's
 // kernel adds into this matrix at any time.
 // ctx->fused_zero: 0 never, 1 wherever a kernel carries the zeroing warp, 2 (default) where it was measured to pay:
-// the Q2 quadrilateral MASS kernel in the shape 4 + 8 + 3 + 1 (one expansion set; zero + mass on the bench workload
-// 1.78 -> 1.59 ms, DRAM traffic 9.2 -> 7.0 GB).  Not: Q2 stiffness (its heavier expansion needs the two sets: 1.84 ->
-// 1.90 ms in that shape, 1.98 ms as 4 + 5 + 6 + 1), Q1 quadrilaterals (0.86 -> 0.89 ms), Q1 hexahedra (a 15th warp, no
-// register cost, correct -- tests/test_gpu_fused_zero.py -- but 128^3 cells, 8 points: 0.707 vs 0.587 ms; config 3 at
-// 256^3: 2.42 vs 2.38 ms per step).  profiles/r2s3/call2_*.log, call5_*.log
+// the Q2 quadrilateral kernels in the shape 4 + 8 + 3 + 1 (one expansion set, the wait for the zeroed ranges in the
+// first moment warp; bench workload, zero + assemble: mass 1.78 -> 1.54 ms, stiffness 1.83 -> 1.77 ms, DRAM traffic
+// 9.2 -> 7.0 GB per matrix; as 4 + 5 + 6 + 1 with the wait in the expansion warps, round 1: 1.96 / 1.98 ms).  Not: Q1
+// quadrilaterals (0.84 -> 0.93 ms), Q1 hexahedra (a 15th warp, no register cost, correct -- tests/test_gpu_fused_zero.py
+// -- but 128^3 cells, 8 points: 0.707 vs 0.587 ms; config 3 at 256^3: 2.42 vs 2.38 ms per step).
+// profiles/r2s3/call2_*.log, call5_*.log, call10_*.log
 static bool fused_zero_possible(const cq_ctx* ctx, const KParams& P) {
   return P.zero_req && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
 }
@@ -255,7 +256,7 @@ struct StagedShape {
 #define CQ_MOMENT_LONG2 48  // bench workload, mean 40, loses 4 % in it; U{40..80}, mean 60, gains 23 % (Q2) / 4 % (Q1))
 #endif
 #ifndef CQ_MOMENT_NMW2Z  // Q2 quadrilaterals with the zeroing warp: moment warps / expansion sets (4 + NMW2Z + 3 NXS2Z + 1 <= 16;
-#define CQ_MOMENT_NMW2Z 8  // 4 + 5 + 6 + 1: zero + mass 1.96, zero + stiffness 1.98 ms; 4 + 8 + 3 + 1: 1.59 / 1.90 ms)
+#define CQ_MOMENT_NMW2Z 8  // 4 + 5 + 6 + 1: zero + mass 1.96, zero + stiffness 1.98 ms; 4 + 8 + 3 + 1: 1.54 / 1.77 ms)
 #endif
 #ifndef CQ_MOMENT_NXS2Z
 #define CQ_MOMENT_NXS2Z 1
@@ -326,7 +327,7 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
           // take the place of the second expansion set: 4 + 8 + 3 + 1
           constexpr int NMW = T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2;
           constexpr int NXW = (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1);
-          if (fused_zero_ok(ctx, P, T::DEG == 2 && T::FORM_ID == CQ_FORM_MASS))
+          if (fused_zero_ok(ctx, P, T::DEG == 2))
             return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 2 ? CQ_MOMENT_NMW2Z : NMW), (T::DEG == 2 ? CQ_MOMENT_NXS2Z * 3 : NXW), true, CQ_MOMENT_NPP, 1>(ctx, P, s);
           // long rules: as on hexahedra, the serial point loops bind -> more moment warps (Q1 4 + 10 + 2, Q2 4 + 9 + 3:
           // one expansion set) and four points in flight per lane.  1024^2 cells: Q2 stiffness U{200..300} points per

@@ -420,6 +420,12 @@ __global__ void __launch_bounds__((NPW + NCW) * 32, 1) assemble_staged_kernel(co
 // XT: row-owned expansion with the transposed scatter (RowTile, cq_moment.cuh); NXW = sets * (DEG + 1)
 // NPP: producer warps per stage slot
 // ZW: 1 = one more warp that zeroes the matrix ahead of the scatter (fused zeroEntries, cq_zero.cuh)
+// 1: the wait for the zeroed ranges sits in the first moment warp (which has slack) instead of the expansion warps (which
+// are the critical path of a one-set kernel): zero + Q2 stiffness 1.89 -> 1.77 ms, zero + Q2 mass 1.59 -> 1.54 ms
+// (profiles/r2s3/call10_zero_wait_in_moment_warp.log)
+#ifndef CQ_ZWAIT_IN_MOMENT
+#define CQ_ZWAIT_IN_MOMENT 1
+#endif
 template <class T, int G, int NPW, int NMW, int NXW, bool XT = false, int NPP = 1, int ZW = 0>
 __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble_moment_split_kernel(const KParams P) {
   constexpr int CB = 32;
@@ -503,6 +509,18 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
           }
         }
         __syncwarp();
+#if CQ_ZWAIT_IN_MOMENT
+        // fused zeroEntries: the first moment warp holds its arrival until every CTA has zeroed this wave's ranges
+        // (the CTAs' zeroing warps go through the waves in order, so the counter of this wave covers the earlier ones);
+        // the expansion warps then scatter without looking at the counters
+        if (ZW && P.zero_hi != nullptr && warp == NPW * NPP && nent >= 0) {
+          if (lane == 0) {
+            const unsigned* zd = P.zero_done + (rnd * NPW + s);
+            while (ld_relaxed_u32(zd) < gridDim.x) __nanosleep(64);
+          }
+          __syncwarp();
+        }
+#endif
         if (lane == 0) mbar_arrive(&mom_bar[s]);  // also passes the end marker on
       }
       if (++s == NPW) {
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
     // scatter of wave = rnd * NPW + s, every range up to this wave's must be complete on all CTAs.  This set saw the
     // waves <= wave - NXS complete in its previous iteration, so it looks at the counters of the last NXS waves; they
     // are loaded one iteration ahead (normally complete long ago: the load is off the critical path).
-    const bool fz = ZW && P.zero_hi != nullptr;  // ZW == 0: all of this folds away
+    const bool fz = ZW && P.zero_hi != nullptr && !CQ_ZWAIT_IN_MOMENT;  // ZW == 0: all of this folds away
     const long long waves = (num_stages + gridDim.x - 1) / gridDim.x;
     const unsigned zexpect = gridDim.x;
     unsigned zs[NXS];

@@ -204,8 +204,9 @@ int64_t cq_ctx_launch_count(const cq_ctx* ctx);
 int cq_ctx_set_variant(cq_ctx* ctx, int variant);
 /* cq_assemble_matrix_zero zeroes inside the persistent moment kernels (cooperative launch) instead of a memset
  * before them: 1 wherever a kernel can (mass / stiffness on quadrilaterals and Q1 hexahedra), 0 never, -1 = the
- * default: where it was measured to pay (the Q2 quadrilateral mass kernel: zero + assemble 1.78 -> 1.59 ms on the
- * bench workload; the other kernels are bound by their load/store pipe and lose).  Same result either way. */
+ * default: where it was measured to pay (the Q2 quadrilateral kernels: zero + assemble 1.78 -> 1.54 ms (mass) and
+ * 1.83 -> 1.77 ms (stiffness) on the bench workload; the Q1 kernels are bound by their load/store pipe and lose).
+ * Same result either way. */
 int cq_ctx_set_fused_zero(cq_ctx* ctx, int on);
 
 /* ---- the hot path (device pointers) ---------------------------------------------------- */
@@ -217,8 +218,8 @@ int cq_assemble_matrix(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mes
  * kernels the zeroing runs inside the kernel, a few stages ahead of the scatter, so the zeroed lines
  * are still in L2 when the element tensors arrive and each line of the matrix crosses the HBM
  * interface once instead of three times (memset write, read-modify-write) -- when the ctx has the
- * fused zeroing applies (cq_ctx_set_fused_zero; by default on the Q2 quadrilateral mass kernel only: it
- * moves 7.0 instead of 9.2 GB per Q2 matrix, but the other kernels are no faster for it,
+ * fused zeroing applies (cq_ctx_set_fused_zero; by default on the Q2 quadrilateral kernels only: it
+ * moves 7.0 instead of 9.2 GB per Q2 matrix, but the Q1 kernels are no faster for it,
  * profiles/r1/fused_zero_study.md, profiles/r2s3/).  Otherwise, for every other kernel, for lists long
  * enough for ticketed stages (hexahedra), and for a matrix with peer rows, a memset runs first.  Same result as memset + cq_assemble_matrix. */
 int cq_assemble_matrix_zero(cq_ctx* ctx, const cq_form_desc* form, const cq_mesh* mesh,

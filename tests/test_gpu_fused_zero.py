@@ -106,7 +106,7 @@ def test_fused_zero_other_kernels_fall_back_to_memset():
 
 @pytest.mark.parametrize("mode", [False, None], ids=["off", "default"])
 def test_zero_in_call_without_fused_zeroing(mode):
-    """Fused zeroing off / the library's default policy (in the kernel for Q2 quadrilateral mass matrices, memset + kernel
+    """Fused zeroing off / the library's default policy (in the kernel for Q2 quadrilateral matrices, memset + kernel
     otherwise)."""
     asm.set_fused_zero(mode)
     mesh = _mesh(2, 60)

@@ -438,7 +438,6 @@ def test_device_resident_coefficient(cuda_backend, oracle_backend):
         assert f.device_array.is_cuda
         f.array[:] = 0.0  # the device copy is what counts now
         dev = cuda_backend.vector(lf, [qr])
-        assert np.array_equal(host, dev)
-        assert close(dev, ref)
+        assert close(dev, host) and close(dev, ref)  # (the adds are floating-point atomics: equal up to summation order)
         f.device_array = torch.zeros_like(f.device_array)
         assert np.all(cuda_backend.vector(lf, [qr]) == 0.0)
