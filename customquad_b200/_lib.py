@@ -34,10 +34,12 @@ class QuadratureDesc(C.Structure):
 
 class CsrDesc(C.Structure):
     _fields_ = [("num_rows", C.c_int64), ("nnz", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p),
-                ("peer_row0", C.c_int64), ("peer_rowstart", C.c_void_p), ("flags", C.c_int32), ("pad_", C.c_int32)]  # fmt: skip
+                ("peer_row0", C.c_int64), ("peer_rowstart", C.c_void_p), ("flags", C.c_int32), ("pad_", C.c_int32),
+                ("zero_keep_lo", C.c_int64), ("zero_keep_hi", C.c_int64)]  # fmt: skip
 
-    def __init__(self, num_rows=0, nnz=0, indptr=None, indices=None, values=None, peer_row0=None, peer_rowstart=None, flags=0):
-        super().__init__(num_rows, nnz, indptr, indices, values, num_rows if peer_row0 is None else peer_row0, peer_rowstart, flags, 0)
+    def __init__(self, num_rows=0, nnz=0, indptr=None, indices=None, values=None, peer_row0=None, peer_rowstart=None, flags=0, zero_keep=(0, 0)):
+        super().__init__(num_rows, nnz, indptr, indices, values, num_rows if peer_row0 is None else peer_row0, peer_rowstart, flags, 0,
+                         int(zero_keep[0]), int(zero_keep[1]))
 
 
 CQ_CSR_PEER_TARGET = 1

@@ -259,7 +259,8 @@ def assemble_ghost_penalty(V, facets, betas: float, A: CSRMatrix) -> CSRMatrix:
 def _csr_desc(A: CSRMatrix):
     return _lib.CsrDesc(A.shape[0], A.nnz, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data),
                         getattr(A, "peer_row0", None), _ptr(getattr(A, "peer_rowstart", None)),
-                        _lib.CQ_CSR_PEER_TARGET if getattr(A, "peer_target", False) else 0)
+                        _lib.CQ_CSR_PEER_TARGET if getattr(A, "peer_target", False) else 0,
+                        getattr(A, "zero_keep", None) or (0, 0))
 
 
 def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: str = "form", zero: bool | None = None) -> CSRMatrix:
@@ -271,8 +272,9 @@ def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: st
     (accumulate) for a given A.
 
     Multi-GPU: a matrix whose rows receive a neighbour rank's peer scatter (``SlabExchange.enable_peer_scatter``; the
-    neighbour's kernels add into it over NVLink at any time between two fences) is zeroed with the protocol
-    zero -> fence -> assemble; the caller completes it with ``exchange_matrix`` (the second fence) before reading.
+    neighbour's kernels add into its interface rows over NVLink at any time between two fences) is zeroed with the
+    protocol zero the interface rows -> fence -> zero the rest and assemble (one call, ``cq_csr.zero_keep_*``); the
+    caller completes it with ``exchange_matrix`` (the second fence) before reading.
     Every rank has to make the same calls in the same order."""
     assert form.rank == 2
     L = _lib.load()
@@ -287,10 +289,16 @@ def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: st
         A = create_matrix(form, cells, zero=not zero)
     csr = _csr_desc(A)
     if zero and getattr(A, "peer_exchange", None) is not None:
-        # peer scatter (either side): the zeroing of every rank's matrix must be complete before any rank's kernel adds
-        A.data.zero_()
+        # peer scatter (either side): the slots a neighbour's kernels add into -- the interface rows, A.zero_keep -- must be
+        # zero on every rank before any rank's kernel adds: zero them, fence; the rest of the matrix only this rank's
+        # kernels touch, and the first call zeroes it (cq_assemble_matrix_zero skips the kept range)
+        keep = getattr(A, "zero_keep", None)
+        if keep is not None and ids:
+            A.data[keep[0] : keep[1]].zero_()
+        elif A.peer_target or not ids:
+            A.data.zero_()
+            zero = False
         A.peer_exchange.fence(dev)
-        zero = False
     if zero and not ids:
         A.data.zero_()
     for i, _id in enumerate(ids):  # qr tuples are matched to integrals by position (:26,42)

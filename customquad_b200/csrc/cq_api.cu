@@ -437,13 +437,22 @@ static int assemble_matrix_impl(cq_ctx* ctx, const cq_form_desc* form, const cq_
   if (!A || !A->indptr || !A->indices || !A->values) { set_error("CSR arrays null"); return CQ_ERR_INVALID; }
   if (A->num_rows != space->num_dofs * form->bs) { set_error("CSR rows %lld != num_dofs*bs %lld", (long long)A->num_rows, (long long)(space->num_dofs * form->bs)); return CQ_ERR_INVALID; }
   if (int rc = set_device(ctx)) return rc;
-  if (qr->num_entries == 0)
-    return zero_first ? check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * (size_t)A->nnz, static_cast<cudaStream_t>(stream)), "zeroEntries") : CQ_OK;
-  if (zero_first && (A->flags & CQ_CSR_PEER_TARGET)) {
-    set_error("this matrix receives a neighbour rank's peer scatter: zero it, fence, then assemble (cq_peer_fence / SlabExchange.fence)");
+  const bool keep = A->zero_keep_hi > A->zero_keep_lo;
+  if (keep && (A->zero_keep_lo < 0 || A->zero_keep_hi > A->nnz)) { set_error("zero_keep range outside [0, nnz]"); return CQ_ERR_INVALID; }
+  if (qr->num_entries == 0) {
+    if (!zero_first) return CQ_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!keep) return check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * (size_t)A->nnz, s), "zeroEntries");
+    if (int rc = check_cuda(cudaMemsetAsync(A->values, 0, sizeof(double) * (size_t)A->zero_keep_lo, s), "zeroEntries")) return rc;
+    return check_cuda(cudaMemsetAsync(A->values + A->zero_keep_hi, 0, sizeof(double) * (size_t)(A->nnz - A->zero_keep_hi), s), "zeroEntries");
+  }
+  if (zero_first && (A->flags & CQ_CSR_PEER_TARGET) && !keep) {
+    set_error("this matrix receives a neighbour rank's peer scatter: zero the interface rows, fence, then assemble with cq_csr.zero_keep_* naming them (cq_peer_fence / SlabExchange.fence)");
     return CQ_ERR_UNSUPPORTED;
   }
   P.zero_req = zero_first ? 1 : 0;
+  P.zero_keep_lo = keep ? A->zero_keep_lo : 0;
+  P.zero_keep_hi = keep ? A->zero_keep_hi : 0;
   P.num_dofs = space->num_dofs;
   P.nnz = A->nnz;
   P.indptr = A->indptr; P.indices = A->indices; P.values = A->values;

@@ -47,6 +47,7 @@ struct KParams {
   // fused A.zeroEntries() (cq_assemble_matrix_zero, cq_zero.cuh): the kernel itself zeroes `values` just ahead of
   // the scatter, so the REDs hit zeroed lines that are still in L2 instead of reading a memset's lines back from HBM
   int zero_req;                          // 1: values are uninitialised, zero them (in the kernel, or by a memset)
+  long long zero_keep_lo, zero_keep_hi;  // ... except values[zero_keep_lo, zero_keep_hi) (cq_csr.zero_keep_*: zeroed by the caller before its fence)
   int zero_ahead;                        // waves zeroed ahead of the scatter
   long long nnz;
   const long long* __restrict__ zero_hi; // [waves] values[0 .. zero_hi[k]) covers every slot the waves <= k touch; null: no fused zeroing

@@ -81,6 +81,10 @@ static int choose_dynamic(cq_ctx* ctx, KParams& P, const int64_t num_stages, con
 static int prezero(KParams& P, cudaStream_t s) {
   if (!P.zero_req) return CQ_OK;
   P.zero_req = 0;
+  if (P.zero_keep_hi > P.zero_keep_lo) {  // all but the kept range (cq_csr.zero_keep_*)
+    if (int rc = check_cuda(cudaMemsetAsync(P.values, 0, sizeof(double) * (size_t)P.zero_keep_lo, s), "zeroEntries")) return rc;
+    return check_cuda(cudaMemsetAsync(P.values + P.zero_keep_hi, 0, sizeof(double) * (size_t)(P.nnz - P.zero_keep_hi), s), "zeroEntries");
+  }
   return check_cuda(cudaMemsetAsync(P.values, 0, sizeof(double) * (size_t)P.nnz, s), "zeroEntries");
 }
 
@@ -145,8 +149,10 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
 // quadrilaterals (0.84 -> 0.93 ms), Q1 hexahedra (a 15th warp, no register cost, correct -- tests/test_gpu_fused_zero.py
 // -- but 128^3 cells, 8 points: 0.707 vs 0.587 ms; config 3 at 256^3: 2.42 vs 2.38 ms per step).
 // profiles/r2s3/call2_*.log, call5_*.log, call10_*.log
+// (a matrix with peer rows qualifies: the zeroing touches this rank's own value array only, and the slots a neighbour
+// adds into are excluded by the caller's zero_keep range)
 static bool fused_zero_possible(const cq_ctx* ctx, const KParams& P) {
-  return P.zero_req && P.peer_rowstart == nullptr && aligned16(P.values) && ctx->coop_launch;
+  return P.zero_req && aligned16(P.values) && ctx->coop_launch;
 }
 static bool fused_zero_ok(const cq_ctx* ctx, const KParams& P, const bool pays = false) {
   return (ctx->fused_zero == 1 || (ctx->fused_zero == 2 && pays)) && fused_zero_possible(ctx, P);
@@ -187,7 +193,7 @@ static int launch_moment_split(cq_ctx* ctx, KParams P, cudaStream_t s) {
   const int64_t num_stages = (P.num_entries + CB - 1) / CB;
   const int grid = (int)(num_stages < ctx->num_sms ? num_stages : ctx->num_sms);
   if (P.zero_req) {
-    // fused zeroEntries (cq_zero.cuh); not with peer rows (the neighbour's kernel adds into this matrix at any time)
+    // fused zeroEntries (cq_zero.cuh)
     if (ZW && fused_zero_possible(ctx, P)) {  // the caller chose this instantiation by the policy (fused_zero_ok)
       if (int rc = prepare_fused_zero(ctx, P, T::N, grid, s)) return rc;
       void* args[] = {(void*)&P};

@@ -32,7 +32,7 @@ template <class TQ2, int NPW>
 static int launch_owner_q2hex(cq_ctx* ctx, const KParams& P, cudaStream_t s, bool* done) {
   *done = false;
   constexpr int N = TQ2::N;
-  if (!P.zero_req || P.bs < 2 || P.bs > 3 || P.peer_rowstart != nullptr || ctx->variant != 0 || P.num_dofs <= 0) return CQ_OK;
+  if (!P.zero_req || P.bs < 2 || P.bs > 3 || P.peer_rowstart != nullptr || P.zero_keep_hi > P.zero_keep_lo || ctx->variant != 0 || P.num_dofs <= 0) return CQ_OK;
   if (P.num_entries >= (1LL << 26) || P.num_dofs >= 0x7fffffffLL) return CQ_OK;  // (k * 32 + li) and the pair offsets are 32-bit
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t nd1 = (size_t)P.num_dofs + 1;

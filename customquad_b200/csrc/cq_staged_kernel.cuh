@@ -464,13 +464,13 @@ __global__ void __launch_bounds__((NPW * NPP + NMW + NXW + ZW) * 32, 1) assemble
     constexpr int ZB = 4;
     const long long waves = (num_stages + gridDim.x - 1) / gridDim.x;
     const int zahead = P.zero_ahead;
-    zero_share(P.values, __ldg(P.zero_hi + waves - 1), P.nnz, blockIdx.x, gridDim.x, lane);  // rows no entry touches
+    zero_share_keep(P.values, __ldg(P.zero_hi + waves - 1), P.nnz, P.zero_keep_lo, P.zero_keep_hi, blockIdx.x, gridDim.x, lane);  // rows no entry touches
     long long hi_prev = 0;
     for (long long kz0 = 0; kz0 < waves; kz0 += ZB) {
       const long long kz1 = kz0 + ZB < waves ? kz0 + ZB : waves;
       const long long hi = __ldg(P.zero_hi + kz1 - 1);  // before the pacing wait: off the critical path
       while (zero_progress < kz1 - 1 - zahead) __nanosleep(128);
-      zero_share(P.values, hi_prev, hi, blockIdx.x, gridDim.x, lane);
+      zero_share_keep(P.values, hi_prev, hi, P.zero_keep_lo, P.zero_keep_hi, blockIdx.x, gridDim.x, lane);
       hi_prev = hi;
       __threadfence();  // the zero stores are performed (gpu scope) before the signals
       __syncwarp();

@@ -55,6 +55,25 @@ CQ_DEVINL void zero_share(double* values, const long long lo, const long long hi
   }
 }
 
+// ... leaving values[klo, khi) alone (cq_csr.zero_keep_*: the interface rows of a peer scatter, zeroed by the caller
+// before its fence -- the neighbour's kernels may already have added into them)
+CQ_DEVINL void zero_share_keep(double* values, const long long lo, const long long hi, const long long klo, const long long khi,
+                               const long long part, const long long nparts, const int lane) {
+  if (khi <= klo || hi <= klo || lo >= khi) {
+    zero_share(values, lo, hi, part, nparts, lane);
+    return;
+  }
+  if (lo < klo) zero_share(values, lo, klo, part, nparts, lane);
+  long long b = khi;
+  if (b < hi) {
+    if (b & 1) {  // the 16-byte stores of zero_share start at an even index
+      if (part == 0 && lane == 0) values[b] = 0.0;
+      ++b;
+    }
+    zero_share(values, b, hi, part, nparts, lane);
+  }
+}
+
 // ---- setup kernels -------------------------------------------------------------------------------------------
 // one block per wave: raw[wave] = max(end of the last (blocked) CSR row the wave's cells touch), rounded up to 4
 template <int DUMMY = 0>

@@ -236,11 +236,14 @@ class SlabExchange:
         dist.all_gather_object(flags, ok, group=self.group)
         if not all(flags):
             A.peer_row0, A.peer_rowstart = None, None
+            A.zero_keep = None
             return False
         self.peer = True
         # the owner side: a neighbour's kernels add into this matrix at any time between two fences, so zeroing it
         # needs the zero -> fence -> assemble -> fence protocol (assemble_matrix(..., zero=True) follows it)
         A.peer_target = self.has_down
+        # the value slots the lower neighbour adds into: this rank's interface rows (cq_csr.zero_keep_lo / hi)
+        A.zero_keep = tuple(int(v) for v in _to_numpy(A.indptr[[self.recv_row0, self.recv_row0 + self.line]])) if self.has_down else None
         A.peer_exchange = self
         setup_peer_fence(dev, self.group)
         return True

@@ -23,6 +23,7 @@ class CSRMatrix:
         self.peer_row0 = None
         self.peer_rowstart = None
         self.peer_target = False    # a neighbour's kernels add into this matrix (cq_csr.flags & CQ_CSR_PEER_TARGET)
+        self.zero_keep = None       # ... into these value slots (its interface rows): cq_csr.zero_keep_lo / hi
         self.peer_exchange = None   # the SlabExchange whose fence orders the zeroing against the neighbours
 
     @property

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CQ_B200_ABI_VERSION 4
+#define CQ_B200_ABI_VERSION 5
 
 /* ---- status codes ------------------------------------------------------------------ */
 typedef enum cq_status {
@@ -178,10 +178,18 @@ typedef struct cq_csr {
   int64_t peer_row0;
   const int64_t* peer_rowstart;
   /* CQ_CSR_PEER_TARGET: a neighbour rank's kernels add into `values` over NVLink (this rank is the owner side of
-   * a peer scatter).  Zeroing such a matrix has to be ordered against the neighbour by the caller (zero, fence,
-   * assemble, fence): cq_assemble_matrix_zero / the *_host entry points refuse it with CQ_ERR_UNSUPPORTED. */
+   * a peer scatter).  Zeroing such a matrix has to be ordered against the neighbour by the caller: zero the slots
+   * the neighbour adds into, fence, assemble, fence.  cq_assemble_matrix_zero accepts it only with a non-empty
+   * zero_keep range (below); the *_host entry points refuse it with CQ_ERR_UNSUPPORTED. */
   int32_t flags;
   int32_t pad_;
+  /* cq_assemble_matrix_zero leaves values[zero_keep_lo, zero_keep_hi) alone and zeroes the rest (ABI 5).  For the
+   * owner side of a peer scatter: the slots of the interface rows, which the caller zeroed BEFORE the fence that
+   * precedes this call -- the neighbour's kernels may already have added into them, while every other slot of the
+   * matrix is touched by this rank's kernels only and can be zeroed by the call (memset, or inside the kernel).
+   * Empty (lo >= hi, e.g. both 0) when unused. */
+  int64_t zero_keep_lo;
+  int64_t zero_keep_hi;
 } cq_csr;
 
 #define CQ_CSR_PEER_TARGET 1

@@ -12,7 +12,7 @@ STRUCTS = {
     "cq_mesh": ("MeshDesc", ["num_cells", "num_nodes", "geom_dofmap", "coords", "flags"]),
     "cq_space": ("SpaceDesc", ["num_dofs", "dofmap", "coeffs", "elem_pos"]),
     "cq_quadrature": ("QuadratureDesc", ["num_entries", "num_points", "cells", "offsets", "pts", "weights", "normals", "plane_entries", "plane_tiles", "pad_"]),
-    "cq_csr": ("CsrDesc", ["num_rows", "nnz", "indptr", "indices", "values", "peer_row0", "peer_rowstart", "flags", "pad_"]),
+    "cq_csr": ("CsrDesc", ["num_rows", "nnz", "indptr", "indices", "values", "peer_row0", "peer_rowstart", "flags", "pad_", "zero_keep_lo", "zero_keep_hi"]),
     "cq_matrix_job": ("MatrixJob", ["form", "space", "A", "values_host"]),
     "cq_circle": ("CircleDesc", ["xmin", "h", "n", "center", "radius", "n1", "pad_", "g", "gw"]),
     "cq_sphere": ("SphereDesc", ["xmin", "h", "n", "center", "radius", "n1", "axis", "g", "gw", "gu", "gwu"]),

@@ -34,8 +34,9 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, s), f"{s} declared in include/cq_b200.h but not exported"
     L.cq_abi_version.restype = ctypes.c_int
     # 2: cq_csr.peer_row0 / peer_rowstart, cq_ipc_*; 3: cq_assemble_matrix_zero, cq_ctx_set_fused_zero, cq_circle_*, cq_sphere_*;
-    # 4: cq_csr.flags, cq_assemble_matrices_host, cq_comm_*, cq_exchange_offrank*, cq_allreduce_sum, cq_peer_fence*
-    assert L.cq_abi_version() == 4
+    # 4: cq_csr.flags, cq_assemble_matrices_host, cq_comm_*, cq_exchange_offrank*, cq_allreduce_sum, cq_peer_fence*;
+    # 5: cq_csr.zero_keep_lo / zero_keep_hi, cq_ctx_set_fused_zero(-1)
+    assert L.cq_abi_version() == 5
     assert set(_lib._SIGNATURES) == set(declared_symbols())
 
 
