@@ -140,8 +140,7 @@ static int launch_staged(cq_ctx* ctx, KParams P, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "assemble_staged_kernel launch");
 }
 
-// Can the persistent moment kernels zero the matrix themselves (cq_zero.cuh)?  Not with peer rows: the neighbour's
-// kernel adds into this matrix at any time.
+// Can / should the persistent moment kernels zero the matrix themselves (cq_zero.cuh)?
 // ctx->fused_zero: 0 never, 1 wherever a kernel carries the zeroing warp, 2 (default) where it was measured to pay:
 // the Q2 quadrilateral kernels in the shape 4 + 8 + 3 + 1 (one expansion set, the wait for the zeroed ranges in the
 // first moment warp; bench workload, zero + assemble: mass 1.78 -> 1.54 ms, stiffness 1.83 -> 1.77 ms, DRAM traffic
@@ -333,13 +332,14 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
           // take the place of the second expansion set: 4 + 8 + 3 + 1
           constexpr int NMW = T::DEG == 1 ? CQ_MOMENT_NMW : CQ_MOMENT_NMW2;
           constexpr int NXW = (T::DEG == 1 ? CQ_MOMENT_NXS1 : CQ_MOMENT_NXS2) * (T::DEG + 1);
-          if (fused_zero_ok(ctx, P, T::DEG == 2))
+          const bool long_rules = P.num_points > (int64_t)CQ_MOMENT_LONG2 * P.num_entries;  // (their shape below gains more: memset + it)
+          if (fused_zero_ok(ctx, P, T::DEG == 2 && !long_rules))
             return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 2 ? CQ_MOMENT_NMW2Z : NMW), (T::DEG == 2 ? CQ_MOMENT_NXS2Z * 3 : NXW), true, CQ_MOMENT_NPP, 1>(ctx, P, s);
           // long rules: as on hexahedra, the serial point loops bind -> more moment warps (Q1 4 + 10 + 2, Q2 4 + 9 + 3:
           // one expansion set) and four points in flight per lane.  1024^2 cells: Q2 stiffness U{200..300} points per
           // cell 3.70 -> 2.11 ms (0.29 -> 0.51 of the HBM roofline), Q2 mass U{80..120} 1.57 -> 0.91, Q1 stiffness
           // U{80..120} 1.03 -> 0.66 (0.40 -> 0.63); profiles/r2s3/call3_quad_long_shape_unroll_nitsche_sets.log
-          if (P.num_points > (int64_t)CQ_MOMENT_LONG2 * P.num_entries)
+          if (long_rules)
             return launch_moment_split<T, CQ_MOMENT_SG, 4, (T::DEG == 1 ? 10 : 9), T::DEG + 1, true, CQ_MOMENT_NPP, 0>(ctx, P, s);
           return launch_moment_split<T, CQ_MOMENT_SG, 4, NMW, NXW, true, CQ_MOMENT_NPP, 0>(ctx, P, s);
         }
