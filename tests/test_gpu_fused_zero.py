@@ -126,3 +126,37 @@ def test_fused_zero_empty_list_zeroes():
     B.data.fill_(float("nan"))
     cq.assemble_matrix(forms.mass(V), [(np.zeros(0, dtype=np.int32), [], [])], A=B, zero=True)
     assert float(B.data.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("mode", [False, None, True], ids=["memset", "default", "in-kernel"])
+@pytest.mark.parametrize("tdim,degree", [(2, 1), (2, 2), (3, 1)])
+def test_zero_keep_range_is_left_alone(tdim, degree, mode):
+    """cq_csr.zero_keep_lo / hi (ABI 5): the zeroing call leaves that range of value slots alone -- the interface rows of a
+    peer scatter, which the caller zeroed before its fence and a neighbour may already have added into -- and zeroes
+    everything else, by memset or inside the kernel."""
+    import torch
+
+    asm.set_fused_zero(mode)
+    mesh = _mesh(tdim, 40 if tdim == 2 else 12)
+    V = _space(mesh, degree, 1)
+    form = forms.mass(V)
+    qr = synthetic_ragged(np.arange(mesh.num_cells, dtype=np.int32), tdim, 3, 11, seed=4)
+    A = asm.create_matrix(form)
+    cq.assemble_matrix(form, [qr], A=A)
+    ref = A.data.cpu().numpy()
+    B = asm.create_matrix(form, zero=False)
+    ip = B.indptr.cpu().numpy()
+    r0 = B.shape[0] // 3
+    for lo, hi in ((int(ip[r0]), int(ip[r0 + 37])), (int(ip[5]) + 1, int(ip[9]) + 3), (0, int(ip[3]))):  # aligned or not
+        B.zero_keep = (lo, hi)
+        B.data.fill_(float("nan"))
+        B.data[lo:hi] = 7.0  # "already added into by the neighbour"
+        cq.assemble_matrix(form, [qr], A=B, zero=True)
+        torch.cuda.synchronize()
+        b = B.data.cpu().numpy()
+        assert not np.isnan(b).any()
+        want = ref.copy()
+        want[lo:hi] += 7.0
+        assert np.max(np.abs(b - want)) <= RTOL * np.max(np.abs(want))
+        assert np.array_equal(b[:lo] == 0.0, ref[:lo] == 0.0) and np.array_equal(b[hi:] == 0.0, ref[hi:] == 0.0)
+    B.zero_keep = None
