@@ -275,6 +275,12 @@ struct StagedShape {
 #ifndef CQ_MOMENT_NPW3_SHORT  // ... for rules of at most 12 points per cell on average
 #define CQ_MOMENT_NPW3_SHORT 6
 #endif
+#ifndef CQ_MOMENT_NMW3_SHORT  // ... its moment warps and expansion sets: 6 + 6 + 4 = 16 warps (128^3 cells, 8 points: stiffness
+#define CQ_MOMENT_NMW3_SHORT 6  // 0.503 -> 0.470 ms, mass 0.495 -> 0.486 ms; three expansion sets instead, 6 + 4 + 6: 0.500 / 0.506)
+#endif
+#ifndef CQ_MOMENT_NXS3_SHORT
+#define CQ_MOMENT_NXS3_SHORT CQ_MOMENT_NXS3
+#endif
 #ifndef CQ_MOMENT_NMW3
 #define CQ_MOMENT_NMW3 4
 #endif
@@ -361,11 +367,11 @@ static int launch_auto(cq_ctx* ctx, const KParams& P, cudaStream_t s) {
         // short rules (the 8-point bulk rule of config 5): the stages are small and the ring is bound by the stage
         // rate, not by bytes -> six slots (measured on 128^3 cells, 8 points: stiffness 0.513 -> 0.475 ms, mass
         // 0.491 -> 0.466 ms; with U{8..27} points six slots no longer hold a stage and cost 0.60 -> 0.80 ms)
-        // (fused zeroEntries: one more warp, 15 or 13 in all, still 128 registers)
+        // (fused zeroEntries: one more warp -- 6 + 4 + 4 + 1 = 15 or 4 + 4 + 4 + 1 = 13 in all, still 128 registers)
         if (P.num_points <= 12 * P.num_entries) {
           if (fused_zero_ok_static(ctx, P, CQ_MOMENT_NPW3_SHORT))
             return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3, 1>(ctx, P, s);
-          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3, CQ_MOMENT_NXS3 * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
+          return launch_moment_split<T, CQ_MOMENT_G3, CQ_MOMENT_NPW3_SHORT, CQ_MOMENT_NMW3_SHORT, CQ_MOMENT_NXS3_SHORT * 2, true, CQ_MOMENT_NPP3>(ctx, P, s);
         }
         // long rules (real cut cells carry ~110 points in 3-D, config 3): the kernel is bound by the serial point
         // loops of its moment lanes, not by bytes (4 moment warps: 0.27 of the HBM roofline at U{40..60} points per cell,

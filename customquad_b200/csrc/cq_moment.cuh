@@ -244,6 +244,10 @@ CQ_DEVINL void moment_accumulate3(const StageMeta<T, CB>& M, const int e, const 
   }
 }
 
+#ifndef CQ_NITSCHE_UNROLL  // points in flight per lane in the Nitsche moment-set loop (hexahedra 96^3, U{4..16} / U{8..27} surface
+#define CQ_NITSCHE_UNROLL 2  // points per cell: 1: 0.472 / 0.569 ms, 2: 0.483 / 0.586, 4: 0.516 / 0.624 -- but on the real surface rules
+#endif                      // of config 3 one point in flight costs 0.32 -> 0.36 ms, so two)
+constexpr int kNitscheUnroll = CQ_NITSCHE_UNROLL;
 // Nitsche: lane r of the entry's group of four owns moment set r (weights w, w n_0, w n_1 (, w n_2)) and runs
 // over ALL points of the entry: no cross-lane reduction, and the point itself is a shared-memory broadcast.
 template <class T, int CB>
@@ -258,7 +262,7 @@ CQ_DEVINL void moment_accumulate_sets(StageMeta<T, CB>& M, const int e, const bo
   const double* pp = M.pts[e];
   const double* wp = M.w[e];
   const double* np_ = M.nrm[e];
-#pragma unroll 2
+#pragma unroll kNitscheUnroll
   for (int q = 0; q < nq; ++q) {
     double w = wp[q];
     if (r > 0) w *= np_[DIM * q + (r - 1)];
