@@ -936,17 +936,18 @@ def run_gpu(args):
         # at N > 1, the fence
         kern.append({"kernel": name, "ms": ms, "algorithmic_bytes": ab, "achieved_gbs": ab / ms / 1e6, "frac": ab / ms / 1e6 / peak,
                      "zeroing": "inside this kernel (ms includes it and the two setup kernels of the zeroing ranges)" if in_kernel else "memset before the kernel (a separate launch, not in ms)",
-                     "ms_add_only": ms_add, "frac_add_only": ab / ms_add / 1e6 / peak,
+                     "in_kernel_zeroing": in_kernel, "ms_add_only": ms_add, "frac_add_only": ab / ms_add / 1e6 / peak,
                      "ms_in_step": per_form_ms[i], "frac_in_step": ab / per_form_ms[i] / 1e6 / peak,
                      "nnz": A.nnz, "cells_per_s": C_cells / ms * 1e3})  # fmt: skip
     dom = max(kern, key=lambda k: k["ms"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom["kernel"])
+        tj = json.load(open(tp))  # Q2 kernels: the zeroing kernel's traffic, or the add-only kernel's (_<name>_add_only)
+        traffic = tj.get(dom["kernel"]) if dom["in_kernel_zeroing"] else tj.get("_" + dom["kernel"] + "_add_only", tj.get(dom["kernel"]))
     ab_step = sum(k["algorithmic_bytes"] for k in kern)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src, "frac_add_only": dom["frac_add_only"],
                 "basis": "the kernel the timed step runs for this form; where it zeroes the matrix itself (per_kernel[i].zeroing) its time includes the zeroing, for which the algorithmic bytes give no credit -- per_kernel[i].frac_add_only is the add-only kernel on a zeroed matrix, the basis of round 1's 0.66",
                 "step": {"algorithmic_bytes": ab_step, "ms": ms_step, "frac": ab_step / ms_step / 1e6 / peak, "what": "all four forms, zeroing included"},
                 "per_kernel": kern}  # fmt: skip
