@@ -256,6 +256,18 @@ def assemble_ghost_penalty(V, facets, betas: float, A: CSRMatrix) -> CSRMatrix:
     return A
 
 
+def peer_zero_plan(keep, peer_target: bool, has_integrals: bool):
+    """zeroEntries of a matrix that takes part in a peer scatter: (what to zero BEFORE the fence, does the first assembly
+    call zero the rest).  "keep": only the slots a neighbour adds into (``A.zero_keep``), the call zeroes everything else
+    (cq_csr.zero_keep_*); "all": the whole matrix, the call only adds; None: nothing -- no neighbour writes into this
+    matrix (the lowest rank of the slab partition), so the call may zero all of it after the fence."""
+    if keep is not None and has_integrals:
+        return "keep", True
+    if peer_target or not has_integrals:
+        return "all", False
+    return None, True
+
+
 def _csr_desc(A: CSRMatrix):
     return _lib.CsrDesc(A.shape[0], A.nnz, _ptr(A.indptr), _ptr(A.indices), _ptr(A.data),
                         getattr(A, "peer_row0", None), _ptr(getattr(A, "peer_rowstart", None)),
@@ -293,11 +305,11 @@ def assemble_matrix(form: Form, qr_data, A: CSRMatrix | None = None, pattern: st
         # zero on every rank before any rank's kernel adds: zero them, fence; the rest of the matrix only this rank's
         # kernels touch, and the first call zeroes it (cq_assemble_matrix_zero skips the kept range)
         keep = getattr(A, "zero_keep", None)
-        if keep is not None and ids:
+        before, zero = peer_zero_plan(keep, A.peer_target, bool(ids))
+        if before == "keep":
             A.data[keep[0] : keep[1]].zero_()
-        elif A.peer_target or not ids:
+        elif before == "all":
             A.data.zero_()
-            zero = False
         A.peer_exchange.fence(dev)
     if zero and not ids:
         A.data.zero_()

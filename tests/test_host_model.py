@@ -198,3 +198,15 @@ def test_slab_meshes_carry_the_global_coordinates_bit_for_bit():
         s = cqdist.make_slab(P3, n3, r, 3)
         lo = s.first - s.ghost
         assert np.array_equal(g.geometry.x[:, 2].reshape(17, 4, 5)[lo : lo + s.mesh.shape[2] + 1].reshape(-1), s.mesh.geometry.x[:, 2])
+
+
+def test_peer_zero_plan():
+    """assemble_matrix(..., zero=True) on a matrix of a peer scatter: what is zeroed before the fence (customquad_b200/
+    assemble.py; the reference zeroes the whole Mat and lets PETSc's stash exchange order the rest, assemble_matrix.py:20)."""
+    from customquad_b200.assemble import peer_zero_plan
+
+    assert peer_zero_plan((10, 50), True, True) == ("keep", True)      # owner side: interface rows now, the rest in the call
+    assert peer_zero_plan(None, False, True) == (None, True)           # lowest rank: nobody writes into it
+    assert peer_zero_plan(None, True, True) == ("all", False)          # a target without a known range: the old protocol
+    assert peer_zero_plan((10, 50), True, False) == ("all", False)     # no integral to carry the zeroing
+    assert peer_zero_plan(None, False, False) == ("all", False)
